@@ -1,0 +1,216 @@
+// Batched CG on (I + gamma A*A) x = rhs and the fused DDS data-consistency step,
+// expressed as a fixed launch sequence on the caller's stream (CUDA-graph
+// capturable: no allocation, no synchronisation, no host<->device traffic).
+//
+// Follows reference src/utils/cg.py:11-39 step by step:
+//   r = rhs - op(x); p = r; rr = ||r||^2
+//   repeat n_iter: d = op(p); alpha = rr/<p,d>; x += alpha p; r -= alpha d;
+//                  rr' = ||r||^2; beta = rr'/rr; p = r + beta p
+// with op(v) = v + gamma*A*(A v) (src/samplers/utils.py:188-189).
+// Launches per iteration: fp_joseph, bp_pixel(+axpy,+<p,d>), cg_update_xr,
+// cg_update_p (the last p-update is skipped: its result is never read).
+#include "scd_internal.cuh"
+#include <algorithm>
+
+struct CgLayout {
+    size_t img, sino, part_stride;
+    size_t off_q, off_r, off_p, off_d, off_b, off_xh, off_part, total;
+};
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static CgLayout cg_layout(const scd_geom *g, int batch)
+{
+    CgLayout L;
+    L.img = (size_t)g->n0 * g->n1;
+    L.sino = (size_t)g->n_angles * g->n_det;
+    const int nbp = scd_bp_ctas_per_sample(g, batch);
+    const int nvec = scd_vec_blocks_per_sample((int64_t)L.img);
+    L.part_stride = (size_t)std::max(nbp, nvec);
+    size_t o = 0;
+    L.off_q = o;  o += align256(L.sino * batch * 4);
+    L.off_r = o;  o += align256(L.img * batch * 4);
+    L.off_p = o;  o += align256(L.img * batch * 4);
+    L.off_d = o;  o += align256(L.img * batch * 4);
+    L.off_b = o;  o += align256(L.img * batch * 4);    // rhs of the fused step
+    L.off_xh = o; o += align256(L.img * batch * 4);    // CG iterate of the fused step
+    L.off_part = o; o += align256(3 * L.part_stride * batch * 4);
+    L.total = o;
+    return L;
+}
+
+extern "C" size_t scd_cg_workspace_bytes(const scd_geom_t *g, int batch)
+{
+    if (!g || batch <= 0) return 0;
+    return cg_layout(g, batch).total;
+}
+
+int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs, float gamma,
+               int n_iter, int batch, void *work, size_t work_bytes, cudaStream_t st)
+{
+    if (!g || !x || !x_in || !rhs || !work) { scd_set_error("scd_cg: null argument"); return SCD_E_INVALID; }
+    if (batch <= 0) return 0;
+    if (n_iter < 0) { scd_set_error("scd_cg: n_iter < 0"); return SCD_E_INVALID; }
+    if (((uintptr_t)work & 255) != 0) { scd_set_error("scd_cg: workspace must be 256-byte aligned"); return SCD_E_INVALID; }
+    const CgLayout L = cg_layout(g, batch);
+    if (work_bytes < L.total) {
+        scd_set_error("scd_cg: workspace too small (%zu < %zu bytes)", work_bytes, L.total);
+        return SCD_E_WORKSPACE;
+    }
+    char *w = (char *)work;
+    float *q = (float *)(w + L.off_q), *r = (float *)(w + L.off_r);
+    float *p = (float *)(w + L.off_p), *d = (float *)(w + L.off_d);
+    float *part = (float *)(w + L.off_part);
+    const int ps = (int)L.part_stride;
+    float *rr_a = part, *rr_b = part + (size_t)ps * batch, *pd = part + 2 * (size_t)ps * batch;
+    const int nbp = scd_bp_ctas_per_sample(g, batch);
+    const int nvec = scd_vec_blocks_per_sample((int64_t)L.img);
+    const float gs = gamma * (float)g->adj_scale;
+    int rc;
+
+    // r = rhs - x - gamma A*(A x);  p = r;  rr = ||r||^2
+    if ((rc = scd_launch_fp(g, x_in, q, batch, 0, g->n_angles, st))) return rc;
+    BpEpilogue e0;
+    e0.c_acc = -gs; e0.add1 = x_in; e0.c1 = -1.f; e0.add2 = rhs; e0.c2 = 1.f;
+    e0.out2 = p; e0.dot_part = rr_a; e0.dot_stride = ps; e0.dot_with_add1 = 0;
+    if ((rc = scd_launch_bp(g, q, r, batch, 0, g->n_angles, e0, st))) return rc;
+    float *rr_old = rr_a, *rr_new = rr_b;
+    int rr_old_n = nbp;
+
+    for (int it = 0; it < n_iter; ++it) {
+        // d = p + gamma A*(A p);  pd = <p,d>
+        if ((rc = scd_launch_fp(g, p, q, batch, 0, g->n_angles, st))) return rc;
+        BpEpilogue e1;
+        e1.c_acc = gs; e1.add1 = p; e1.c1 = 1.f; e1.add2 = nullptr; e1.c2 = 0.f;
+        e1.out2 = nullptr; e1.dot_part = pd; e1.dot_stride = ps; e1.dot_with_add1 = 1;
+        if ((rc = scd_launch_bp(g, q, d, batch, 0, g->n_angles, e1, st))) return rc;
+        // the first update reads the start iterate and writes the result buffer
+        if ((rc = scd_launch_cg_update_xr(it == 0 ? x_in : x, x, r, p, d, rr_old, rr_old_n, pd, nbp, ps, rr_new,
+                                          batch, (int64_t)L.img, st))) return rc;
+        if (it + 1 < n_iter) {
+            if ((rc = scd_launch_cg_update_p(p, r, rr_new, nvec, rr_old, rr_old_n, ps, batch,
+                                             (int64_t)L.img, st))) return rc;
+        }
+        std::swap(rr_old, rr_new);
+        rr_old_n = nvec;
+    }
+    if (n_iter == 0 && x != x_in)
+        SCD_CUDA(cudaMemcpyAsync(x, x_in, L.img * batch * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int scd_cg(const scd_geom_t *g, float *x, const float *rhs, double gamma, int n_iter,
+                      int batch, void *work, size_t work_bytes, void *stream)
+{
+    return scd_cg_run(g, x, x, rhs, (float)gamma, n_iter, batch, work, work_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
+                      int angle_lo, int angle_hi, void *stream)
+{
+    return scd_launch_fp(g, img, sino, batch, angle_lo, angle_hi, (cudaStream_t)stream);
+}
+
+extern "C" int scd_bp(const scd_geom_t *g, const float *sino, float *out, int batch,
+                      int angle_lo, int angle_hi, float c_acc, const float *addend, float c_add,
+                      void *stream)
+{
+    BpEpilogue e;
+    e.c_acc = c_acc; e.add1 = addend; e.c1 = c_add; e.add2 = nullptr; e.c2 = 0.f;
+    e.out2 = nullptr; e.dot_part = nullptr; e.dot_stride = 0; e.dot_with_add1 = 0;
+    return scd_launch_bp(g, sino, out, batch, angle_lo, angle_hi, e, (cudaStream_t)stream);
+}
+
+extern "C" int scd_tweedie_rhs(const float *x, const float *s, const float *atb, const float *t,
+                               const float *abar, int n_table, double gamma, float *xhat0,
+                               float *b, int batch, int64_t numel, void *stream)
+{
+    if (!x || !s || !t || !abar || !xhat0 || (b && !atb)) {
+        scd_set_error("scd_tweedie_rhs: null argument"); return SCD_E_INVALID;
+    }
+    if (n_table < 1) { scd_set_error("scd_tweedie_rhs: empty alpha-bar table"); return SCD_E_INVALID; }
+    return scd_launch_tweedie_rhs(x, s, atb, t, abar, n_table, (float)gamma, xhat0, b, batch, numel,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" int scd_ddim(const float *xhat, const float *s, const float *eps, const float *t,
+                        const float *t_prev, const float *abar, int n_table, double eta, float *out,
+                        int batch, int64_t numel, void *stream)
+{
+    if (!xhat || !s || !eps || !t || !t_prev || !abar || !out) {
+        scd_set_error("scd_ddim: null argument"); return SCD_E_INVALID;
+    }
+    if (n_table < 1) { scd_set_error("scd_ddim: empty alpha-bar table"); return SCD_E_INVALID; }
+    // `tbeta.pow(2)*eta**2`: eta**2 is evaluated in Python (fp64) and then rounded
+    return scd_launch_ddim(xhat, s, eps, t, t_prev, abar, n_table, (float)eta, (float)(eta * eta), out,
+                           batch, numel, (cudaStream_t)stream);
+}
+
+extern "C" int scd_dds_step(const scd_geom_t *g, const float *x, const float *s, const float *atb,
+                            const float *eps, const float *t, const float *t_prev,
+                            const float *abar, int n_table, double gamma, double eta, int n_iter,
+                            float *x_next, float *xhat0, int batch, void *work, size_t work_bytes,
+                            void *stream)
+{
+    if (!g || !x || !s || !atb || !eps || !t || !t_prev || !abar || !x_next || !xhat0 || !work) {
+        scd_set_error("scd_dds_step: null argument"); return SCD_E_INVALID;
+    }
+    if (batch <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const CgLayout L = cg_layout(g, batch);
+    if (work_bytes < L.total) {
+        scd_set_error("scd_dds_step: workspace too small (%zu < %zu bytes)", work_bytes, L.total);
+        return SCD_E_WORKSPACE;
+    }
+    char *w = (char *)work;
+    float *b = (float *)(w + L.off_b), *xh = (float *)(w + L.off_xh);
+    const int64_t numel = (int64_t)L.img;
+    int rc;
+    // xhat0 = Tweedie(x, s);  b = xhat0 + gamma*A*y
+    if ((rc = scd_launch_tweedie_rhs(x, s, atb, t, abar, n_table, (float)gamma, xhat0, b, batch, numel, st)))
+        return rc;
+    // CG starts from xhat0 but must not overwrite it (the predictor returns it)
+    if ((rc = scd_cg_run(g, xhat0, xh, b, (float)gamma, n_iter, batch, work, work_bytes, st))) return rc;
+    return scd_launch_ddim(xh, s, eps, t, t_prev, abar, n_table, (float)eta, (float)(eta * eta), x_next,
+                           batch, numel, st);
+}
+
+// ------------------------------------------------------ host-buffer calls ---
+static int host_roundtrip(const scd_geom_t *g, const float *in_host, size_t in_elems,
+                          float *out_host, size_t out_elems, int batch, bool forward)
+{
+    if (!g || !in_host || !out_host) { scd_set_error("scd_*_host: null argument"); return SCD_E_INVALID; }
+    if (batch <= 0) return 0;
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t st = nullptr;
+    int rc = 0;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return scd_cuda_fail(e, "stream create");
+    if ((e = cudaMalloc(&d_in, in_elems * 4)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
+    if ((e = cudaMalloc(&d_out, out_elems * 4)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
+    if ((e = cudaMemcpyAsync(d_in, in_host, in_elems * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = scd_cuda_fail(e, "H2D"); goto done; }
+    if (forward) rc = scd_fp(g, d_in, d_out, batch, 0, g->n_angles, st);
+    else rc = scd_bp(g, d_in, d_out, batch, 0, g->n_angles, (float)g->adj_scale, nullptr, 0.f, st);
+    if (rc) goto done;
+    if ((e = cudaMemcpyAsync(out_host, d_out, out_elems * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = scd_cuda_fail(e, "D2H"); goto done; }
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = scd_cuda_fail(e, "sync"); goto done; }
+done:
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+extern "C" int scd_fp_host(const scd_geom_t *g, const float *img_host, float *sino_host, int batch)
+{
+    if (!g) { scd_set_error("scd_fp_host: null handle"); return SCD_E_INVALID; }
+    return host_roundtrip(g, img_host, (size_t)batch * g->n0 * g->n1, sino_host,
+                          (size_t)batch * g->n_angles * g->n_det, batch, true);
+}
+
+extern "C" int scd_bp_host(const scd_geom_t *g, const float *sino_host, float *img_host, int batch)
+{
+    if (!g) { scd_set_error("scd_bp_host: null handle"); return SCD_E_INVALID; }
+    return host_roundtrip(g, sino_host, (size_t)batch * g->n_angles * g->n_det, img_host,
+                          (size_t)batch * g->n0 * g->n1, batch, false);
+}

@@ -1,0 +1,159 @@
+// Geometry handle: host-side derivation of the per-angle projector constants
+// (fp64) and their upload.  Follows the index-space specification of
+// SURVEY.md Appendix A, which restates what SimpleTrafo.__init__
+// (reference src/physics/trafo.py:17-34) obtains from ODL.
+#include "scd_internal.cuh"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+static thread_local char    g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void scd_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int scd_cuda_fail(cudaError_t e, const char *what)
+{
+    scd_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return -(int)e;
+}
+
+void scd_count_launch(int n) { g_launches += n; }
+
+extern "C" const char *scd_last_error_string(void) { return g_err; }
+extern "C" const char *scd_version(void) { return "scd_b200 0.1 (sm_100a)"; }
+extern "C" int64_t scd_launch_count(void) { return g_launches; }
+extern "C" void scd_launch_count_reset(void) { g_launches = 0; }
+
+extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
+{
+    if (!d || !out) { scd_set_error("scd_geom_create: null argument"); return SCD_E_INVALID; }
+    *out = nullptr;
+    if (d->n0 < 1 || d->n1 < 1 || d->n_angles < 1 || d->n_det < 2 || !d->angles ||
+        !(d->dx > 0) || !(d->ds > 0)) {
+        scd_set_error("scd_geom_create: invalid geometry (n0=%d n1=%d n_angles=%d n_det=%d dx=%g ds=%g)",
+                      d->n0, d->n1, d->n_angles, d->n_det, d->dx, d->ds);
+        return SCD_E_INVALID;
+    }
+    if (d->n0 > 8192 || d->n1 > 8192 || d->n_det > 16384) {
+        scd_set_error("scd_geom_create: geometry too large for the fp32 index arithmetic");
+        return SCD_E_INVALID;
+    }
+    int dev = 0, ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        scd_set_error("scd_geom_create: no CUDA device (%s); this library has no CPU path",
+                      cudaGetErrorString(e));
+        return SCD_E_NODEVICE;
+    }
+    SCD_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    SCD_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        scd_set_error("scd_geom_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                      dev, prop.major, prop.minor);
+        return SCD_E_NODEVICE;
+    }
+
+    scd_geom *g = (scd_geom *)calloc(1, sizeof(scd_geom));
+    if (!g) { scd_set_error("out of host memory"); return SCD_E_INVALID; }
+    g->n0 = d->n0; g->n1 = d->n1; g->n_angles = d->n_angles; g->n_det = d->n_det;
+    g->x_min = d->x_min; g->y_min = d->y_min; g->dx = d->dx;
+    g->s_min = d->s_min; g->ds = d->ds; g->adj_scale = d->adj_scale;
+    g->device = dev;
+    g->sm_count = prop.multiProcessorCount;
+    g->smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+    const int na = d->n_angles;
+    g->h_fp = (FpAngle *)malloc(sizeof(FpAngle) * na);
+    g->h_bp = (BpAngle *)malloc(sizeof(BpAngle) * na);
+    g->h_order = (int *)malloc(sizeof(int) * na);
+    std::vector<int> c0, c1;
+    for (int i = 0; i < na; ++i) {
+        const double phi = d->angles[i];
+        const double cs = std::cos(phi), sn = std::sin(phi);
+        FpAngle &f = g->h_fp[i];
+        if (std::fabs(sn) > std::fabs(cs)) {
+            // march along axis 0 (x), interpolate along axis 1 (y)
+            f.cls = 0;
+            f.a = d->ds / (sn * d->dx);
+            f.b = -cs / sn;
+            f.c = ((d->s_min + 0.5 * d->ds - (d->x_min + 0.5 * d->dx) * cs) / sn - d->y_min) / d->dx - 0.5;
+            f.scale = (float)(d->dx / std::fabs(sn));
+            c0.push_back(i);
+        } else {
+            // march along axis 1 (y), interpolate along axis 0 (x)
+            f.cls = 1;
+            f.a = d->ds / (cs * d->dx);
+            f.b = -sn / cs;
+            f.c = ((d->s_min + 0.5 * d->ds - (d->y_min + 0.5 * d->dx) * sn) / cs - d->x_min) / d->dx - 0.5;
+            f.scale = (float)(d->dx / std::fabs(cs));
+            c1.push_back(i);
+        }
+        BpAngle &b = g->h_bp[i];
+        b.ci = d->dx * cs / d->ds;
+        b.si = d->dx * sn / d->ds;
+        b.oi = ((d->x_min + 0.5 * d->dx) * cs + (d->y_min + 0.5 * d->dx) * sn - d->s_min) / d->ds - 0.5;
+    }
+    g->n_cls0 = (int)c0.size();
+    std::copy(c0.begin(), c0.end(), g->h_order);
+    std::copy(c1.begin(), c1.end(), g->h_order + c0.size());
+
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&g->d_fp, sizeof(FpAngle) * na)) != cudaSuccess ||
+        (ce = cudaMalloc(&g->d_bp, sizeof(BpAngle) * na)) != cudaSuccess ||
+        (ce = cudaMalloc(&g->d_order, sizeof(int) * na)) != cudaSuccess ||
+        (ce = cudaMemcpy(g->d_fp, g->h_fp, sizeof(FpAngle) * na, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(g->d_bp, g->h_bp, sizeof(BpAngle) * na, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMemcpy(g->d_order, g->h_order, sizeof(int) * na, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        scd_geom_destroy(g);
+        return scd_cuda_fail(ce, "scd_geom_create upload");
+    }
+    *out = g;
+    return 0;
+}
+
+extern "C" int scd_geom_destroy(scd_geom_t *g)
+{
+    if (!g) return 0;
+    if (g->d_fp) cudaFree(g->d_fp);
+    if (g->d_bp) cudaFree(g->d_bp);
+    if (g->d_order) cudaFree(g->d_order);
+    free(g->h_fp); free(g->h_bp); free(g->h_order);
+    free(g);
+    return 0;
+}
+
+extern "C" int scd_geom_info(const scd_geom_t *g, int32_t *n0, int32_t *n1,
+                             int32_t *n_angles, int32_t *n_det)
+{
+    if (!g) { scd_set_error("scd_geom_info: null handle"); return SCD_E_INVALID; }
+    if (n0) *n0 = g->n0;
+    if (n1) *n1 = g->n1;
+    if (n_angles) *n_angles = g->n_angles;
+    if (n_det) *n_det = g->n_det;
+    return 0;
+}
+
+extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
+{
+    if (!g || !key) { scd_set_error("scd_set_tuning: null argument"); return SCD_E_INVALID; }
+    if (!strcmp(key, "fp_samples")) g->tune_fp_samples = value;
+    else if (!strcmp(key, "fp_angles")) g->tune_fp_angles = value;
+    else if (!strcmp(key, "fp_rows")) g->tune_fp_rows = value;
+    else if (!strcmp(key, "fp_threads")) g->tune_fp_threads = value;
+    else if (!strcmp(key, "bp_samples")) g->tune_bp_samples = value;
+    else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
+    else { scd_set_error("scd_set_tuning: unknown key '%s'", key); return SCD_E_INVALID; }
+    return 0;
+}

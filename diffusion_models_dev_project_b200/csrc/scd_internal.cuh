@@ -1,0 +1,111 @@
+// Internal declarations shared by the translation units of libscd_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "scd_b200.h"
+
+// ---------------------------------------------------------------- errors ---
+void scd_set_error(const char *fmt, ...);
+int  scd_cuda_fail(cudaError_t e, const char *what);   // records + returns -(int)e
+void scd_count_launch(int n = 1);
+
+#define SCD_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return scd_cuda_fail(e__, #call);             \
+    } while (0)
+
+#define SCD_LAUNCH_CHECK(name)                                                \
+    do {                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ != cudaSuccess) return scd_cuda_fail(e__, name);              \
+        scd_count_launch();                                                   \
+    } while (0)
+
+// -------------------------------------------------------------- geometry ---
+// Forward projector, per angle.  In "tile coordinates" the ray of detector bin
+// j crosses marching row r at interpolation-axis position
+//     u(r, j) = a*j + b*r + c          (pixel-index units, pixel 0 centred at 0)
+// class 0: |sin| > |cos|, march along axis 0 (r = k0), interpolate along axis 1
+// class 1: otherwise,      march along axis 1 (r = k1), interpolate along axis 0
+struct FpAngle {
+    double a, b, c;     // exact (host fp64) coefficients
+    float  scale;       // dx / max(|cos|,|sin|)
+    int    cls;
+};
+
+// Backprojector, per angle: detector coordinate (bin units, bin 0 centred at
+// 0) of pixel (k0,k1):  v = ci*k0 + si*k1 + oi
+struct BpAngle {
+    double ci, si, oi;
+};
+
+struct scd_geom {
+    int n0, n1, n_angles, n_det;
+    double x_min, y_min, dx, s_min, ds, adj_scale;
+    int device;
+    int sm_count;
+    int smem_optin;       // max dynamic shared memory per block (opt-in), bytes
+    // device tables
+    FpAngle *d_fp;        // [n_angles]
+    BpAngle *d_bp;        // [n_angles]
+    int     *d_order;     // [n_angles] angle ids sorted by (class, index)
+    // host copies
+    FpAngle *h_fp;
+    BpAngle *h_bp;
+    int     *h_order;
+    int n_cls0;           // number of class-0 angles (they come first in order[])
+    // tuning overrides (0 = heuristic)
+    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads;
+    int tune_bp_samples, tune_bp_tile;
+};
+
+// ------------------------------------------------------------ launchers ----
+int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
+                  int angle_lo, int angle_hi, cudaStream_t st);
+
+// Backprojection with fused epilogue:
+//   val  = c_acc*BP + c1*add1 + c2*add2
+//   out  = val; if (out2) out2 = val
+//   if (dot_part): dot_part[b*dot_stride + cta] = sum over the CTA's pixels of
+//        val * (dot_with_add1 ? add1 : val)
+struct BpEpilogue {
+    float c_acc;
+    const float *add1; float c1;
+    const float *add2; float c2;
+    float *out2;
+    float *dot_part; int dot_stride; int dot_with_add1;
+};
+int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
+                  int angle_lo, int angle_hi, const BpEpilogue &ep,
+                  cudaStream_t st);
+// number of dot_part entries per sample the BP launch for this batch writes
+int scd_bp_ctas_per_sample(const scd_geom *g, int batch);
+
+// Vector kernels of the CG recurrences (vec_ops.cu).  *_part arrays hold
+// per-block partial sums [batch][part_stride]; consumers add them in index
+// order (deterministic, no atomics).
+int scd_vec_blocks_per_sample(int64_t numel);
+int scd_launch_cg_update_xr(const float *x_in, float *x, float *r, const float *p, const float *d,
+                            const float *rr_part, int rr_n,
+                            const float *pd_part, int pd_n, int part_stride,
+                            float *rr_new_part, int batch, int64_t numel,
+                            cudaStream_t st);
+int scd_launch_cg_update_p(float *p, const float *r, const float *rr_new_part,
+                           int rr_new_n, const float *rr_old_part, int rr_old_n,
+                           int part_stride, int batch, int64_t numel,
+                           cudaStream_t st);
+int scd_launch_tweedie_rhs(const float *x, const float *s, const float *atb,
+                           const float *t, const float *abar, int n_table,
+                           float gamma, float *xhat0, float *b, int batch,
+                           int64_t numel, cudaStream_t st);
+int scd_launch_ddim(const float *xhat, const float *s, const float *eps,
+                    const float *t, const float *t_prev, const float *abar,
+                    int n_table, float eta, float eta2, float *out, int batch,
+                    int64_t numel, cudaStream_t st);
+
+// x_in: start iterate (read only), x_out: result (may alias x_in)
+int scd_cg_run(const scd_geom *g, const float *x_in, float *x_out, const float *rhs,
+               float gamma, int n_iter, int batch, void *work, size_t work_bytes,
+               cudaStream_t st);

@@ -1,0 +1,316 @@
+"""B200RayTrafo: drop-in for the reference's ``SimpleTrafo`` backed by libscd_b200.so.
+
+Same constructor and attributes as ``SimpleTrafo(im_shape, num_angles, impl)``
+(reference src/physics/trafo.py:17-68): ``im_shape``, ``obs_shape``, ``angles``,
+``trafo``/``__call__``, ``trafo_adjoint``, ``trafo_flat``, ``trafo_adjoint_flat``,
+``fbp`` and ``.to(device)``.  It deliberately has no ``resize`` attribute
+(``hasattr(ray_trafo, 'resize')`` probes, reference exp_utils.py:126,232).
+
+All arithmetic runs in hand-written sm_100a kernels reached through the C ABI
+(include/scd_b200.h); PyTorch only owns the buffers and the stream.  Inputs
+must live on a CUDA device -- there is no CPU path.
+"""
+import ctypes as C
+import threading
+from math import pi
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .. import _lib
+from .base_ray_trafo import BaseRayTrafo
+from .geometry import ParallelBeamGeometry2D
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _GeomHandle:
+    """Owns one ``scd_geom_t*`` (device tables) for one CUDA device."""
+
+    def __init__(self, geom: ParallelBeamGeometry2D, adj_scale: float, device: torch.device):
+        lib = _lib.load()
+        ang = np.ascontiguousarray(geom.angles, dtype=np.float64)
+        desc = _lib.GeomDesc(
+            n0=geom.n0, n1=geom.n1, x_min=geom.x_min, y_min=geom.y_min, dx=geom.dx,
+            n_angles=geom.n_angles, angles=ang.ctypes.data_as(C.POINTER(C.c_double)),
+            n_det=geom.n_det, s_min=geom.s_min, ds=geom.ds, adj_scale=adj_scale)
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.scd_geom_create(C.byref(desc), C.byref(h)), 'scd_geom_create')
+        self.ptr = h
+        self.device = device
+        self._lib = lib
+
+    def __del__(self):
+        try:
+            if getattr(self, 'ptr', None):
+                self._lib.scd_geom_destroy(self.ptr)
+                self.ptr = None
+        except Exception:  # interpreter shutdown
+            pass
+
+
+class _TrafoFn(torch.autograd.Function):
+    """y = A x.  Backward: the unweighted transpose A^T g = A*(g)/c_w (ODL
+    ``OperatorFunction`` convention)."""
+
+    @staticmethod
+    def forward(ctx, x, rt):
+        ctx.rt = rt
+        return rt._fp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        rt = ctx.rt
+        return _AdjointFn.apply(g, rt) * (1.0 / rt.geometry.range_weight), None
+
+
+class _AdjointFn(torch.autograd.Function):
+    """x = A* y.  Backward: c_w * A g."""
+
+    @staticmethod
+    def forward(ctx, y, rt):
+        ctx.rt = rt
+        return rt._bp(y, rt.adj_scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        rt = ctx.rt
+        return _TrafoFn.apply(g, rt) * rt.geometry.range_weight, None
+
+
+class NormalOp:
+    """``op(v) = v + gamma * A*(A v)`` -- the closure every predictor of the
+    reference builds (reference src/samplers/utils.py:188-189, 235-236, 302-303),
+    as an object so that :func:`..utils.cg.cg` can recognise it and run the
+    fused CUDA solve.  Calling it evaluates the operator (autograd-aware)."""
+
+    def __init__(self, ray_trafo, gamma: float):
+        self.ray_trafo = ray_trafo
+        self.gamma = float(gamma)
+
+    def __call__(self, v: Tensor) -> Tensor:
+        rt = self.ray_trafo
+        if isinstance(rt, B200RayTrafo) and not (torch.is_grad_enabled() and v.requires_grad):
+            return rt.normal_apply(v, self.gamma)
+        return v + self.gamma * rt.trafo_adjoint(rt(v))
+
+
+class B200RayTrafo(BaseRayTrafo):
+    """2-D parallel-beam ray transform on B200.
+
+    Parameters
+    ----------
+    im_shape : (int, int)
+    num_angles : int
+    impl : str
+        Accepted for signature compatibility with ``SimpleTrafo``; must be
+        ``'b200'`` (or the reference's ``'odl'`` / ``'iradon'`` names, which
+        select the same kernels -- there is exactly one implementation).
+    adjoint_scaling : {'dphi', 'dphi/ds'}
+        ``A* = adj_scale * sum_i lerp(y[i], t_i(x))``; ``'dphi'`` (default) is the
+        continuous weighted adjoint (kappa = 1 of SURVEY.md §8c), ``'dphi/ds'``
+        the alternative kappa = 1/ds convention.
+    """
+
+    def __init__(self, im_shape, num_angles, impl='b200', adjoint_scaling='dphi'):
+        if impl not in ('b200', 'odl', 'iradon'):
+            raise NotImplementedError(impl)
+        geom = ParallelBeamGeometry2D.from_im_shape(im_shape, num_angles)
+        super().__init__(im_shape=tuple(int(v) for v in im_shape), obs_shape=geom.obs_shape)
+        self.geometry = geom
+        if adjoint_scaling == 'dphi':
+            self.adj_scale = geom.dphi
+        elif adjoint_scaling == 'dphi/ds':
+            self.adj_scale = geom.dphi / geom.ds
+        else:
+            raise ValueError(adjoint_scaling)
+        self._angles = geom.angles
+        self._handles = {}
+        self._work = {}
+        self._hlock = threading.Lock()
+        self._fbp_filter = {}
+
+    # ------------------------------------------------------------ plumbing ---
+    @property
+    def angles(self) -> np.ndarray:
+        return self._angles
+
+    def _handle(self, device: torch.device) -> _GeomHandle:
+        if device.type != 'cuda':
+            raise RuntimeError(
+                'B200RayTrafo works on CUDA tensors only (got %s); there is no CPU fallback' % device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            with self._hlock:
+                h = self._handles.get(idx)
+                if h is None:
+                    h = _GeomHandle(self.geometry, self.adj_scale, torch.device('cuda', idx))
+                    self._handles[idx] = h
+        return h
+
+    def set_tuning(self, device, **kw):
+        """Override launch heuristics (see scd_set_tuning)."""
+        h = self._handle(torch.device(device))
+        for k, v in kw.items():
+            _lib.check(h._lib.scd_set_tuning(h.ptr, k.encode(), int(v)), 'scd_set_tuning')
+
+    @staticmethod
+    def _prep(t: Tensor, tail_shape, what: str) -> Tensor:
+        if t.dim() < 2 or tuple(t.shape[-2:]) != tuple(tail_shape):
+            raise ValueError('%s: expected trailing shape %r, got %r' % (what, tuple(tail_shape), tuple(t.shape)))
+        if t.dtype != torch.float32:
+            raise TypeError('%s: float32 required, got %s' % (what, t.dtype))
+        return t.contiguous()
+
+    def workspace(self, batch: int, device: torch.device) -> Tensor:
+        """Scratch for scd_cg / scd_dds_step (cached per device and batch)."""
+        h = self._handle(device)
+        key = (h.device.index, batch)
+        w = self._work.get(key)
+        if w is None:
+            nbytes = int(h._lib.scd_cg_workspace_bytes(h.ptr, batch))
+            w = torch.empty(nbytes + 256, dtype=torch.uint8, device=h.device)
+            self._work[key] = w
+        return w
+
+    @staticmethod
+    def _aligned(w: Tensor):
+        p = w.data_ptr()
+        off = (-p) % 256
+        return p + off, w.numel() - off
+
+    # ------------------------------------------------------ raw operators ----
+    def _fp(self, x: Tensor, angle_range=None) -> Tensor:
+        x = self._prep(x, self.im_shape, 'trafo')
+        h = self._handle(x.device)
+        lead = x.shape[:-2]
+        batch = int(np.prod(lead)) if len(lead) else 1
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        if (lo, hi) == (0, self.obs_shape[0]):
+            y = torch.empty(*lead, *self.obs_shape, dtype=torch.float32, device=x.device)
+        else:
+            y = torch.zeros(*lead, *self.obs_shape, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(h._lib.scd_fp(h.ptr, x.data_ptr(), y.data_ptr(), batch, lo, hi,
+                                     _stream_ptr(x.device)), 'scd_fp')
+        return y
+
+    def _bp(self, y: Tensor, scale: float, addend: Tensor = None, addend_scale: float = 0.0,
+            angle_range=None) -> Tensor:
+        y = self._prep(y, self.obs_shape, 'trafo_adjoint')
+        h = self._handle(y.device)
+        lead = y.shape[:-2]
+        batch = int(np.prod(lead)) if len(lead) else 1
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        x = torch.empty(*lead, *self.im_shape, dtype=torch.float32, device=y.device)
+        add_ptr = None
+        if addend is not None:
+            addend = self._prep(addend, self.im_shape, 'addend')
+            if addend.shape != x.shape:
+                raise ValueError('addend shape %r != %r' % (tuple(addend.shape), tuple(x.shape)))
+            add_ptr = addend.data_ptr()
+        with torch.cuda.device(y.device):
+            _lib.check(h._lib.scd_bp(h.ptr, y.data_ptr(), x.data_ptr(), batch, lo, hi, float(scale),
+                                     add_ptr, float(addend_scale), _stream_ptr(y.device)), 'scd_bp')
+        return x
+
+    def normal_apply(self, v: Tensor, gamma: float) -> Tensor:
+        """``v + gamma*A*(A v)`` with the axpy fused into the backprojector (no grad)."""
+        q = self._fp(v)
+        return self._bp(q, gamma * self.adj_scale, addend=v, addend_scale=1.0)
+
+    # --------------------------------------------------- reference interface --
+    def trafo(self, x: Tensor) -> Tensor:
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _TrafoFn.apply(x, self)
+        return self._fp(x)
+
+    def trafo_adjoint(self, observation: Tensor) -> Tensor:
+        if torch.is_grad_enabled() and observation.requires_grad:
+            return _AdjointFn.apply(observation, self)
+        return self._bp(observation, self.adj_scale)
+
+    trafo_flat = BaseRayTrafo._trafo_flat_via_trafo
+    trafo_adjoint_flat = BaseRayTrafo._trafo_adjoint_flat_via_trafo_adjoint
+
+    def normal_op(self, gamma: float) -> NormalOp:
+        return NormalOp(self, gamma)
+
+    # ------------------------------------------------------------- solvers ---
+    def cg_solve(self, x0: Tensor, rhs: Tensor, gamma: float, n_iter: int) -> Tensor:
+        """Fused batched CG on ``(I + gamma A*A) x = rhs`` from ``x0`` (no grad).
+        Same recurrences as the reference's ``cg`` (src/utils/cg.py:11-39)."""
+        x0 = self._prep(x0, self.im_shape, 'cg x')
+        rhs = self._prep(rhs, self.im_shape, 'cg rhs')
+        if rhs.shape != x0.shape:
+            raise ValueError('cg: x %r and rhs %r differ in shape' % (tuple(x0.shape), tuple(rhs.shape)))
+        if rhs.device != x0.device:
+            raise ValueError('cg: x and rhs live on different devices')
+        h = self._handle(x0.device)
+        batch = int(np.prod(x0.shape[:-2])) if x0.dim() > 2 else 1
+        x = x0.clone()
+        w = self.workspace(batch, x0.device)
+        wp, wn = self._aligned(w)
+        with torch.cuda.device(x0.device):
+            _lib.check(h._lib.scd_cg(h.ptr, x.data_ptr(), rhs.data_ptr(), float(gamma), int(n_iter), batch,
+                                     wp, wn, _stream_ptr(x0.device)), 'scd_cg')
+        return x
+
+    def dds_step(self, x: Tensor, s: Tensor, atb: Tensor, eps: Tensor, t: Tensor, t_prev: Tensor,
+                 abar: Tensor, gamma: float, eta: float, n_iter: int):
+        """Tweedie -> rhs -> CG -> DDIM in one library call; returns ``(x_next, xhat0)``
+        (reference src/samplers/utils.py:195-218)."""
+        x = self._prep(x, self.im_shape, 'dds x')
+        s = self._prep(s, self.im_shape, 'dds s')
+        atb = self._prep(atb, self.im_shape, 'dds rhs')
+        eps = self._prep(eps, self.im_shape, 'dds eps')
+        for name, v in (('s', s), ('eps', eps)):
+            if v.shape != x.shape:
+                raise ValueError('dds_step: %s shape %r != x shape %r' % (name, tuple(v.shape), tuple(x.shape)))
+        batch = int(np.prod(x.shape[:-2])) if x.dim() > 2 else 1
+        if atb.shape != x.shape:
+            atb = atb.expand_as(x).contiguous()
+        t = t.to(device=x.device, dtype=torch.float32).contiguous()
+        t_prev = t_prev.to(device=x.device, dtype=torch.float32).contiguous()
+        if t.numel() != batch or t_prev.numel() != batch:
+            raise ValueError('dds_step: time steps must have one entry per sample')
+        h = self._handle(x.device)
+        x_next = torch.empty_like(x)
+        xhat0 = torch.empty_like(x)
+        w = self.workspace(batch, x.device)
+        wp, wn = self._aligned(w)
+        with torch.cuda.device(x.device):
+            _lib.check(h._lib.scd_dds_step(
+                h.ptr, x.data_ptr(), s.data_ptr(), atb.data_ptr(), eps.data_ptr(), t.data_ptr(),
+                t_prev.data_ptr(), abar.data_ptr(), int(abar.numel()), float(gamma), float(eta), int(n_iter),
+                x_next.data_ptr(), xhat0.data_ptr(), batch, wp, wn, _stream_ptr(x.device)), 'scd_dds_step')
+        return x_next, xhat0
+
+    # ----------------------------------------------------------------- fbp ---
+    def _ramp(self, device):
+        f = self._fbp_filter.get(device)
+        if f is None:
+            n_det = self.obs_shape[1]
+            n_pad = max(64, 1 << int(np.ceil(np.log2(2 * n_det))))
+            freq = np.fft.rfftfreq(n_pad, d=self.geometry.ds)          # cycles per length unit
+            f = (torch.from_numpy(np.abs(freq)).to(torch.float32).to(device), n_pad)
+            self._fbp_filter[device] = f
+        return f
+
+    def fbp(self, observation: Tensor) -> Tensor:
+        """Ram-Lak filtered back-projection (zero-padded FFT ramp filter, then the
+        pixel-driven backprojector with weight ``dphi``): ``fbp(A x) ~ x``.
+        Counterpart of ``odl.tomo.fbp_op`` used at reference src/physics/trafo.py:34,67;
+        filter recipe as in src/physics/utils.py:11-33."""
+        y = self._prep(observation, self.obs_shape, 'fbp')
+        ramp, n_pad = self._ramp(y.device)
+        spec = torch.fft.rfft(y, n=n_pad, dim=-1)
+        # irfft(rfft(p)*|xi|) is the Riemann sum of (p * h)(s_j) including the ds
+        # factor, so f = int_0^pi (p_theta * h)(x.theta) dtheta ~ dphi * sum_i lerp(...)
+        filt = torch.fft.irfft(spec * ramp, n=n_pad, dim=-1)[..., :self.obs_shape[1]].contiguous()
+        return self._bp(filt, self.geometry.dphi)

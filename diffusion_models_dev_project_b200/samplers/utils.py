@@ -1,0 +1,246 @@
+"""Predictors and update rules of the DDS / SCD reverse sampler.
+
+Call signatures follow reference src/samplers/utils.py (``:159-218`` DDS
+predictor, ``:220-260`` ``_adapt``, ``:280-336`` adapted predictor, ``:338-368``
+``ddim``, ``:370-378`` ``apTweedy``, ``:403-434`` schedule helpers), so that
+``functools.partial`` objects and ``sample_kwargs['predictor']`` dictionaries
+built for the reference work unchanged.
+
+Dispatch rule (no silent fallbacks): with a :class:`B200RayTrafo`, a ``DDPM``
+schedule, CUDA fp32 tensors and no gradient required, the work after the score
+call runs in the fused sm_100a kernels; whenever a gradient is required (SCD
+adaptation) or the schedule is VE/VP, the same formulas run as tensor
+operations, with A / A* still executed by the CUDA projector kernels through
+their autograd Functions.
+"""
+from typing import Dict, Optional, Tuple, Union
+
+import torch
+from torch import Tensor
+
+from .. import fused
+from ..physics.b200_ray_trafo import B200RayTrafo, NormalOp
+from ..utils.cg import cg
+from ..utils.sde import SDE, VESDE, VPSDE, DDPM, _SCORE_PRED_CLASSES
+
+
+# --------------------------------------------------------------- helpers ----
+def _eps_pred_from_s(s, std_t):
+    """Score-matching output -> epsilon prediction (reference :396-400)."""
+    return - std_t * s
+
+
+def _fusable(sde, *tensors) -> bool:
+    if not isinstance(sde, DDPM):
+        return False
+    for t in tensors:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.float32):
+            return False
+        if torch.is_grad_enabled() and t.requires_grad:
+            return False
+    return True
+
+
+def _make_op(ray_trafo, gamma):
+    if isinstance(ray_trafo, B200RayTrafo):
+        return NormalOp(ray_trafo, gamma)
+    return lambda v: v + gamma * ray_trafo.trafo_adjoint(ray_trafo(v))
+
+
+def apTweedy(s: Tensor, x: Tensor, sde: SDE, time_step: Tensor) -> Tensor:
+    """Tweedie denoised estimate ``xhat0 = (x - std_t*eps_hat)/mean_t`` (reference :370-378)."""
+    if _fusable(sde, s, x):
+        return fused.tweedie_rhs(x, s, time_step, sde.alpha_bar_table(x.device))
+    div = sde.marginal_prob_mean(time_step)[:, None, None, None].pow(-1)
+    std_t = sde.marginal_prob_std(time_step)[:, None, None, None]
+    if any(isinstance(sde, c) for c in _SCORE_PRED_CLASSES):
+        s = _eps_pred_from_s(s=s, std_t=std_t)
+    return (x - s * std_t) * div
+
+
+def ddim(sde: SDE, s: Tensor, xhat: Tensor, time_step: Union[Tensor, Tuple[Tensor, Tensor]],
+         step_size: Tensor, eta: float, use_simplified_eqn: bool = False) -> Tensor:
+    """DDIM update (reference :338-368); VE, VP and DDPM branches."""
+    pair = isinstance(time_step, tuple)
+    t = time_step[0] if pair else time_step
+    tminus1 = time_step[1] if pair else time_step - step_size
+    if _fusable(sde, s, xhat):
+        return fused.ddim_ddpm(xhat, s, torch.randn_like(xhat), t, tminus1,
+                               sde.alpha_bar_table(xhat.device), eta)
+    std_t = sde.marginal_prob_std(t=t)[:, None, None, None]
+    if isinstance(sde, VESDE):
+        std_tminus1 = sde.marginal_prob_std(t=tminus1)[:, None, None, None]
+        tbeta = 1 - (std_tminus1.pow(2) * std_t.pow(-2)) if not use_simplified_eqn else torch.tensor(1.)
+        noise_deterministic = - std_tminus1 * std_t * torch.sqrt(1 - tbeta.pow(2) * eta ** 2) * s
+        noise_stochastic = std_tminus1 * eta * tbeta * torch.randn_like(xhat)
+    elif isinstance(sde, (VPSDE, DDPM)):
+        mean_tminus1 = sde.marginal_prob_mean(t=tminus1)[:, None, None, None]
+        mean_t = sde.marginal_prob_mean(t=t)[:, None, None, None]
+        tbeta = ((1 - mean_tminus1.pow(2)) / (1 - mean_t.pow(2))).pow(.5) * \
+            (1 - mean_t.pow(2) * mean_tminus1.pow(-2)).pow(.5)
+        # per-sample NaN -> 0 (the reference zeroes the whole batch if any entry is
+        # NaN, :360; identical whenever all samples share the time step) -- no host sync
+        tbeta = torch.nan_to_num(tbeta, nan=0.0, posinf=float('inf'), neginf=float('-inf'))
+        xhat = xhat * mean_tminus1
+        eps_ = _eps_pred_from_s(s, std_t) if isinstance(sde, VPSDE) else s
+        noise_deterministic = torch.sqrt(1 - mean_tminus1.pow(2) - tbeta.pow(2) * eta ** 2) * eps_
+        noise_stochastic = eta * tbeta * torch.randn_like(xhat)
+    else:
+        raise NotImplementedError
+    return xhat + noise_deterministic + noise_stochastic
+
+
+# ------------------------------------------------------------ predictors ----
+def decomposed_diffusion_sampling_sde_predictor(
+        score, sde: SDE, x: Tensor, rhs: Tensor,
+        time_step: Union[Tensor, Tuple[Tensor, Tensor]],
+        eta: float, gamma: float, step_size: float, cg_kwargs: Dict,
+        datafitscale: Optional[float] = None,  # unused, kept for the call contract
+        use_simplified_eqn: bool = False, ray_trafo=None) -> Tuple[Tensor, Tensor]:
+    """Decomposed diffusion sampling step: score -> Tweedie -> CG data consistency
+    on ``(I + gamma A*A) x = xhat0 + gamma A*y`` -> DDIM.  Returns ``(x_next, xhat0)``
+    -- the second value is the Tweedie estimate, not the CG result (reference :218)."""
+    pair = isinstance(time_step, tuple)
+    t = time_step[0] if pair else time_step
+    with torch.no_grad():
+        s = score(x, t)
+        if pair and isinstance(ray_trafo, B200RayTrafo) and _fusable(sde, s, x, rhs):
+            eps = torch.randn_like(x)
+            x_next, xhat0 = ray_trafo.dds_step(
+                x, s, rhs, eps, t, time_step[1], sde.alpha_bar_table(x.device),
+                gamma=gamma, eta=eta, n_iter=cg_kwargs['max_iter'])
+            return x_next.detach(), xhat0.detach()
+        op = _make_op(ray_trafo, gamma)
+        xhat0 = apTweedy(s=s, x=x, sde=sde, time_step=t)
+        xhat = cg(op=op, x=xhat0, rhs=xhat0 + gamma * rhs, n_iter=cg_kwargs['max_iter'])
+        x = ddim(sde=sde, s=s, xhat=xhat, time_step=time_step, step_size=step_size, eta=eta,
+                 use_simplified_eqn=use_simplified_eqn)
+    return x.detach(), xhat0.detach()
+
+
+_LORA_CLASSES = ('LoraInjectedLinear', 'LoraInjectedConv2d', 'LoraInjectedConv1d')
+
+
+def _lora_modules(score):
+    return [m for m in score.modules() if m.__class__.__name__ in _LORA_CLASSES]
+
+
+def _tune_lora_scale(score, scale: float = 1.0):
+    for m in _lora_modules(score):
+        m.scale = scale
+
+
+def _has_lora(score):
+    return True if _lora_modules(score) else None
+
+
+def _has_lora_active(score):
+    mods = _lora_modules(score)
+    return (mods[0].scale != 0) if mods else None
+
+
+def _adapt(x: Tensor, score, sde: SDE, ray_trafo, loss_fn, time_step: Tensor, rhs: Tensor,
+           num_steps: int, lr: float = 1e-3, gamma: float = 1e-3, n_iter: int = 1,
+           dc_type: str = "cg") -> None:
+    """SCD adaptation: ``num_steps`` Adam steps on the trainable (LoRA / bias)
+    parameters of ``score`` through Tweedie -> data consistency -> loss
+    (reference :220-260).  Gradients flow through A, A* (CUDA kernels via their
+    autograd Functions) and every CG recurrence."""
+    op = _make_op(ray_trafo, gamma)
+    assert _has_lora_active(score=score)
+    score.eval()
+    optim = torch.optim.Adam(score.parameters(), lr=lr)
+    for _ in range(num_steps):
+        optim.zero_grad()
+        s = score(x, time_step)
+        xhat0 = apTweedy(s=s, x=x, sde=sde, time_step=time_step)
+        if dc_type == "cg":
+            xhat = cg(op=op, x=xhat0, rhs=xhat0 + gamma * rhs, n_iter=n_iter)
+        elif dc_type == "dc":
+            xhat = xhat0 - gamma * ray_trafo.trafo_adjoint(ray_trafo(xhat0)) + gamma * rhs
+        elif dc_type == "none":
+            xhat = xhat0
+        else:
+            raise NotImplementedError
+        loss = loss_fn(x=xhat)
+        loss.backward()
+        optim.step()
+
+
+def adapted_ddim_sde_predictor(
+        score, sde: SDE, x: Tensor, time_step: Union[Tensor, Tuple[Tensor, Tensor]],
+        eta: float, step_size: float, adapt_fn, use_adapt: bool = False,
+        datafitscale: Optional[float] = None, use_simplified_eqn: bool = False,
+        ray_trafo=None, add_cg: bool = False, dc_type: str = None, gamma: float = None,
+        cg_kwargs: Dict = None, rhs: Tensor = None) -> Tuple[Tensor, Tensor]:
+    """SCD step (reference :280-336): optional adaptation, Tweedie with the adapted
+    score, optional data consistency (``cg`` | ``gd`` | ``none``), DDIM with the
+    un-adapted score (LoRA scale switched to 0 for that call)."""
+    pair = isinstance(time_step, tuple)
+    t = time_step[0] if pair else time_step
+    if use_adapt:
+        adapt_fn(x=x, time_step=t, ray_trafo=ray_trafo, rhs=rhs, gamma=gamma, n_iter=cg_kwargs['max_iter'])
+    op = _make_op(ray_trafo, gamma)
+    with torch.no_grad():
+        s = score(x, t)
+        xhat0 = apTweedy(s=s, x=x, sde=sde, time_step=t)
+        if add_cg:
+            if dc_type == "cg":
+                xhat = cg(op=op, x=xhat0, rhs=xhat0 + gamma * rhs, n_iter=cg_kwargs['max_iter'])
+            elif dc_type == "gd":
+                xhat = xhat0 - gamma * ray_trafo.trafo_adjoint(ray_trafo(xhat0)) + gamma * rhs
+            elif dc_type == "none":
+                xhat = xhat0
+            else:
+                raise NotImplementedError
+        if _has_lora(score=score):
+            _tune_lora_scale(score=score, scale=0)
+        s = score(x, t)
+        if _has_lora(score=score):
+            _tune_lora_scale(score=score, scale=1.0)
+        x = ddim(sde=sde, s=s, xhat=xhat if add_cg else xhat0, time_step=time_step,
+                 step_size=step_size, eta=eta, use_simplified_eqn=use_simplified_eqn)
+    return x.detach(), xhat0.detach()
+
+
+def wrapper_ddim(score, sde: SDE, x: Tensor, time_step, step_size, datafitscale=1.):
+    """Unconditional DDIM step with eta = 0.85 (reference :436-451)."""
+    t = time_step[0] if isinstance(time_step, tuple) else time_step
+    with torch.no_grad():
+        s = score(x, t).detach()
+        xhat0 = apTweedy(s=s, x=x, sde=sde, time_step=t)
+        x = ddim(sde=sde, s=s, xhat=xhat0, time_step=time_step, step_size=step_size, eta=0.85,
+                 use_simplified_eqn=False)
+    return x.detach(), xhat0.detach()
+
+
+# -------------------------------------------------------------- schedule ----
+def _check_times(times, t_0, num_steps):
+    assert times[0] > times[1], (times[0], times[1])
+    assert times[-1] == -1, times[-1]
+    for t_last, t_cur in zip(times[:-1], times[1:]):
+        assert abs(t_last - t_cur) == 1, (t_last, t_cur)
+    for t in times:
+        assert t >= t_0, (t, t_0)
+        assert t <= num_steps, (t, num_steps)
+
+
+def _schedule_jump(num_steps, travel_length, travel_repeat):
+    """Time-travel schedule; ``[num_steps-1, ..., 0, -1]`` when length = repeat = 1
+    (reference :416-434)."""
+    jumps = {j: travel_repeat - 1 for j in range(0, num_steps - travel_length, travel_length)}
+    t = num_steps
+    time_steps = []
+    while t >= 1:
+        t -= 1
+        time_steps.append(t)
+        if jumps.get(t, 0) > 0:
+            jumps[t] -= 1
+            for _ in range(travel_length):
+                t += 1
+                time_steps.append(t)
+    time_steps.append(-1)
+    _check_times(time_steps, -1, num_steps)
+    return time_steps

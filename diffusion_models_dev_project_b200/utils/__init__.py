@@ -1,0 +1,3 @@
+from .sde import SDE, VESDE, VPSDE, DDPM, _EPSILON_PRED_CLASSES, _SCORE_PRED_CLASSES
+from .metrics import PSNR
+from .cg import cg

@@ -1,0 +1,154 @@
+/*
+ * scd_b200.h -- C ABI of libscd_b200.so
+ *
+ * B200 (sm_100a) implementation of the data-consistency hot path of the
+ * SCD / DDS reverse sampler of educating-dip/diffusion_models_dev_project:
+ *
+ *   A   parallel-beam ray transform, ray-driven Joseph projector
+ *   A*  pixel-driven linear-interpolation backprojector (weighted adjoint)
+ *   CG  batched conjugate gradient on (I + gamma A*A) x = rhs
+ *   Tweedie + rhs, DDIM update (DDPM schedule)
+ *
+ * The reference has no native code: the interfaces these entry points replace
+ * are Python call sites, cited per function below (paths relative to the
+ * reference checkout).  Calling convention:
+ *
+ *   - plain C, no C++/torch types; every buffer is a raw pointer.  Unless a
+ *     function name ends in `_host`, buffers are DEVICE pointers owned by
+ *     the caller (PyTorch), fp32, contiguous:
+ *       image     [batch][n0][n1]            (n1 fastest; axis0 <-> x, axis1 <-> y)
+ *       sinogram  [batch][n_angles][n_det]   (n_det fastest)
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and
+ *     the call returns without synchronising (graph-capture safe: no
+ *     allocation, no sync, no host reads of device memory after create).
+ *   - gamma / eta are passed as double (the Python floats of the reference's
+ *     CLI); kernels round them to fp32 exactly where PyTorch would.
+ *   - return value: 0 on success, < 0 on failure (negated cudaError_t, or
+ *     SCD_E_* below); scd_last_error_string() describes the last failure on
+ *     the calling thread.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef SCD_B200_H
+#define SCD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCD_E_INVALID   (-10001)  /* bad argument                           */
+#define SCD_E_NODEVICE  (-10002)  /* no CUDA device / not sm_100            */
+#define SCD_E_WORKSPACE (-10003)  /* caller workspace too small             */
+
+typedef struct scd_geom scd_geom_t; /* opaque, immutable after create */
+
+/* Geometry description.  Mirrors what SimpleTrafo.__init__ derives through
+ * odl.uniform_discr + odl.tomo.parallel_beam_geometry
+ * (src/physics/trafo.py:17-27): image grid, angle list, detector partition.
+ * adj_scale is the factor applied by A* on top of the plain sum of
+ * interpolated detector values (default of the Python layer: delta_phi).   */
+typedef struct scd_geom_desc {
+    int32_t n0, n1;        /* image shape (axis0 = x, axis1 = y)             */
+    double  x_min, y_min;  /* lower corner of the image domain               */
+    double  dx;            /* pixel size (square pixels)                     */
+    int32_t n_angles;
+    const double *angles;  /* [n_angles] radians, host pointer (copied)      */
+    int32_t n_det;
+    double  s_min;         /* lower edge of the detector partition (= -rho)  */
+    double  ds;            /* detector cell size                             */
+    double  adj_scale;     /* A* = adj_scale * sum_i lerp(sino[i], t_i(x))   */
+} scd_geom_desc;
+
+/* Build the device-side tables for one geometry on the current device.
+ * Replaces: SimpleTrafo.__init__ (src/physics/trafo.py:17-51).              */
+int scd_geom_create(const scd_geom_desc *desc, scd_geom_t **out);
+int scd_geom_destroy(scd_geom_t *g);
+
+/* A: forward projection of angles [angle_lo, angle_hi) (rows outside that
+ * range of `sino` are left untouched; sino always has n_angles rows).
+ * Replaces: SimpleTrafo.trafo -> ODL/ASTRA par_fp (src/physics/trafo.py:58). */
+int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
+           int angle_lo, int angle_hi, void *stream);
+
+/* A*: out = c_acc * BP(sino; angles [lo,hi)) + c_add * addend
+ * where BP is the un-scaled pixel-driven sum; the plain adjoint is
+ * c_acc = adj_scale, addend = NULL.
+ * Replaces: SimpleTrafo.trafo_adjoint -> ODL/ASTRA par_bp
+ * (src/physics/trafo.py:61) and the axpy of `op` (src/samplers/utils.py:188-189). */
+int scd_bp(const scd_geom_t *g, const float *sino, float *out, int batch,
+           int angle_lo, int angle_hi, float c_acc, const float *addend,
+           float c_add, void *stream);
+
+/* Bytes of scratch scd_cg / scd_dds_step need for `batch` samples.           */
+size_t scd_cg_workspace_bytes(const scd_geom_t *g, int batch);
+
+/* Batched CG, fixed n_iter, per-sample alpha/beta, no tolerance test:
+ * solves (I + gamma A*A) x = rhs starting from x (overwritten by the result).
+ * Replaces: cg(op, x, rhs, n_iter) with op(v) = v + gamma*A*(A v)
+ * (src/utils/cg.py:11-39, src/samplers/utils.py:188-189).                    */
+int scd_cg(const scd_geom_t *g, float *x, const float *rhs, double gamma,
+           int n_iter, int batch, void *work, size_t work_bytes, void *stream);
+
+/* DDPM alpha-bar table: abar[k] = prod_{m<k}(1 - beta_m) rounded to fp32, k in
+ * [0, n_table) with abar[0] = 1 (index t+1, so t = -1 -> 1).  Device pointer,
+ * computed by the caller exactly like DDPM._compute_alpha_cumprod
+ * (src/utils/sde.py:172-174).  t / t_prev are DEVICE float arrays [batch]
+ * holding integer-valued time steps, as BaseSampler passes them
+ * (src/samplers/base_sampler.py:83-87).                                      */
+
+/* Tweedie + CG right-hand side in one pass:
+ *   xhat0 = (x - s*sqrt(1-abar_t)) / sqrt(abar_t);  b = xhat0 + gamma*atb
+ * Replaces: apTweedy (src/samplers/utils.py:370-378) + :197.                 */
+int scd_tweedie_rhs(const float *x, const float *s, const float *atb,
+                    const float *t, const float *abar, int n_table,
+                    double gamma, float *xhat0, float *b, int batch,
+                    int64_t numel_per_sample, void *stream);
+
+/* DDIM update for the DDPM schedule:
+ *   out = m' * xhat + sqrt(1 - m'^2 - tbeta^2 eta^2) * s + eta*tbeta*eps
+ * (m' = sqrt(abar_{t_prev}); tbeta as in the reference, NaN -> 0).
+ * Replaces: ddim(...) DDPM branch (src/samplers/utils.py:338-368).           */
+int scd_ddim(const float *xhat, const float *s, const float *eps,
+             const float *t, const float *t_prev, const float *abar,
+             int n_table, double eta, float *out, int batch,
+             int64_t numel_per_sample, void *stream);
+
+/* One whole data-consistency step of the DDS predictor after the score call:
+ * Tweedie -> b -> CG(n_iter) -> DDIM.  x_next and xhat0 are outputs.
+ * Replaces: decomposed_diffusion_sampling_sde_predictor body after score()
+ * (src/samplers/utils.py:195-216).                                           */
+int scd_dds_step(const scd_geom_t *g, const float *x, const float *s,
+                 const float *atb, const float *eps, const float *t,
+                 const float *t_prev, const float *abar, int n_table,
+                 double gamma, double eta, int n_iter, float *x_next,
+                 float *xhat0, int batch, void *work, size_t work_bytes,
+                 void *stream);
+
+/* Host-buffer variants (pageable or pinned host memory): copy in, run, copy
+ * out, synchronise the stream.  These are what a non-PyTorch caller binds.   */
+int scd_fp_host(const scd_geom_t *g, const float *img_host, float *sino_host,
+                int batch);
+int scd_bp_host(const scd_geom_t *g, const float *sino_host, float *img_host,
+                int batch);
+
+/* Introspection used by the tests, the bench and the launch heuristics.      */
+int scd_geom_info(const scd_geom_t *g, int32_t *n0, int32_t *n1,
+                  int32_t *n_angles, int32_t *n_det);
+/* Number of kernels this library has launched on the calling thread since
+ * the last reset (the bench reports it as gpu_launches).                     */
+int64_t scd_launch_count(void);
+void    scd_launch_count_reset(void);
+/* Override launch heuristics (tuning / tests).  key is one of
+ * "fp_samples", "fp_angles", "fp_rows", "bp_samples", "bp_tile"; value 0
+ * restores the heuristic.  Not thread-safe; intended for benchmarks.         */
+int scd_set_tuning(scd_geom_t *g, const char *key, int value);
+
+const char *scd_last_error_string(void);
+const char *scd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCD_B200_H */
