@@ -34,17 +34,33 @@ struct BpParams {
     BpEpilogue ep;
 };
 
+template <int S> struct BpVec;
+template <> struct BpVec<1> { typedef float  T; };
+template <> struct BpVec<2> { typedef float2 T; };
+template <> struct BpVec<4> { typedef float4 T; };
+
+__device__ __forceinline__ void bp_tap(float (&a)[1], float l, float r, float wl, float w)
+{ a[0] = fmaf(r, w, fmaf(l, wl, a[0])); }
+__device__ __forceinline__ void bp_tap(float (&a)[2], float2 l, float2 r, float wl, float w)
+{ a[0] = fmaf(r.x, w, fmaf(l.x, wl, a[0])); a[1] = fmaf(r.y, w, fmaf(l.y, wl, a[1])); }
+__device__ __forceinline__ void bp_tap(float (&a)[4], float4 l, float4 r, float wl, float w)
+{
+    a[0] = fmaf(r.x, w, fmaf(l.x, wl, a[0])); a[1] = fmaf(r.y, w, fmaf(l.y, wl, a[1]));
+    a[2] = fmaf(r.z, w, fmaf(l.z, wl, a[2])); a[3] = fmaf(r.w, w, fmaf(l.w, wl, a[3]));
+}
+
 template <int S, int WY>
 __global__ void __launch_bounds__(32 * WY)
 bp_pixel_kernel(const BpParams P)
 {
+    typedef typename BpVec<S>::T V;
     constexpr int TH = 4 * WY;
     constexpr int NT = 32 * WY;
-    extern __shared__ float smem[];
-    // layout: consts[AC] (float4) | jlo[AC] (int) | seg[S][AC][SEG]
+    extern __shared__ __align__(16) float smem[];
+    // layout: consts[AC] (float4) | jlo[AC] (int, padded to 4) | seg[AC][SEG][S] (samples interleaved)
     float4 *cst = reinterpret_cast<float4 *>(smem);
     int *jlo = reinterpret_cast<int *>(smem + 4 * P.AC);
-    float *seg = smem + 5 * P.AC;
+    float *seg = smem + 4 * P.AC + ((P.AC + 3) & ~3);
     __shared__ float red[S][WY];
 
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5;
@@ -72,44 +88,38 @@ bp_pixel_kernel(const BpParams P)
             const double vmin = v00 + fmin(0.0, A.ci * (double)(TH - 1)) + fmin(0.0, A.si * 31.0);
             const int j0 = (int)floor(vmin) - 1;   // one bin of slack below (fp32 rounding)
             jlo[i] = j0;
-            // z' = (v - j0) - 0.5  (round-to-nearest of z' == floor(v - j0))
-            cst[i] = make_float4((float)A.ci, (float)A.si, (float)(v00 - (double)j0 - 0.5), 0.f);
+            // zf = v - j0 >= 1: floor(zf) = segment index of the left tap
+            cst[i] = make_float4((float)A.ci, (float)A.si, (float)(v00 - (double)j0), 0.f);
         }
         __syncthreads();
-        // ---- stage the detector segments -----------------------------------
+        // ---- stage the detector segments, samples interleaved per bin ----------
         for (int row = wy; row < S * nac; row += WY) {
             const int s = row / nac, i = row - s * nac;
             const int b = b0 + s;
             const int j0 = jlo[i];
             const float *src = P.sino + (size_t)(b < P.batch ? b : 0) * sino_sz +
                                (size_t)(a0 + i) * P.n_det;
-            float *dst = seg + (s * AC + i) * SEG;
+            float *dst = seg + (size_t)i * SEG * S + s;
             for (int e = lane; e < SEG; e += 32) {
                 const int j = j0 + e;
-                dst[e] = (b < P.batch && j >= 0 && j < P.n_det) ? __ldg(src + j) : 0.f;
+                dst[e * S] = (b < P.batch && j >= 0 && j < P.n_det) ? __ldg(src + j) : 0.f;
             }
         }
         __syncthreads();
         // ---- accumulate ----------------------------------------------------
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < nac; ++i) {
             const float4 c = cst[i];
             const float vb = fmaf(lx, c.y, c.z);
-            const float *row = seg + i * SEG;
+            const V *row = reinterpret_cast<const V *>(seg) + (size_t)i * SEG;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const float z = fmaf(ky0 + (float)m, c.x, vb);
-                const float t = z + SCD_MAGIC;
-                const float kf = t - SCD_MAGIC;
-                const float w = (z - kf) + 0.5f;
-                const int k = __float_as_int(t) - SCD_MAGIC_BITS;
-                const float *q = row + k;
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const float f0 = q[s * AC * SEG];
-                    const float f1 = q[s * AC * SEG + 1];
-                    acc[m][s] += fmaf(w, f1 - f0, f0);
-                }
+                const float t = __fadd_rd(z, SCD_MAGIC);                 // floor(z) in the mantissa
+                const float w = z - (t - SCD_MAGIC);
+                const float wl = 1.0f - w;
+                const V *q = row + (__float_as_int(t) - SCD_MAGIC_BITS);
+                bp_tap(acc[m], q[0], q[1], wl, w);
             }
         }
     }
@@ -165,11 +175,14 @@ struct BpConfig { int S, WY, AC, SEG; size_t smem; dim3 grid; };
 static BpConfig bp_choose(const scd_geom *g, int batch, int angle_lo, int angle_hi)
 {
     BpConfig c;
-    c.S = batch >= 64 ? 2 : 1;
+    // measured on B200 (tools/kbench.py --kernel bp --sweep): 64 x 32 tiles are fastest at every
+    // batch size; 4 interleaved samples per thread once the batch provides enough CTAs
+    c.S = batch >= 32 ? 4 : (batch >= 16 ? 2 : 1);
     if (g->tune_bp_samples) c.S = g->tune_bp_samples;
-    c.WY = 8;                                  // 32 x 32 tile, 256 threads
+    if (c.S != 1 && c.S != 2 && c.S != 4) c.S = 1;
+    c.WY = 16;                                 // 64 x 32 tile, 512 threads
     if (g->tune_bp_tile) c.WY = g->tune_bp_tile / 4;
-    if (c.WY != 4 && c.WY != 8 && c.WY != 16) c.WY = 8;
+    if (c.WY != 4 && c.WY != 8 && c.WY != 16) c.WY = 16;
     const int TH = 4 * c.WY;
     double span = 0.0;
     for (int i = angle_lo; i < angle_hi; ++i)
@@ -179,8 +192,9 @@ static BpConfig bp_choose(const scd_geom *g, int batch, int angle_lo, int angle_
     // whole angle range in one chunk when it fits in ~64 KB, else chunks
     c.AC = na;
     const size_t budget = 64 * 1024;
-    while ((size_t)c.AC * (5 + (size_t)c.S * c.SEG) * 4 > budget && c.AC > 8) c.AC = (c.AC + 1) / 2;
-    c.smem = (size_t)c.AC * (5 + (size_t)c.S * c.SEG) * 4;
+    auto bytes = [&](int ac) { return (size_t)(4 * ac + ((ac + 3) & ~3) + (size_t)ac * c.S * c.SEG) * 4; };
+    while (bytes(c.AC) > budget && c.AC > 8) c.AC = (c.AC + 1) / 2;
+    c.smem = bytes(c.AC);
     c.grid = dim3((g->n1 + 31) / 32, (g->n0 + TH - 1) / TH, (batch + c.S - 1) / c.S);
     return c;
 }

@@ -14,7 +14,7 @@
 
 struct CgLayout {
     size_t img, sino, part_stride;
-    size_t off_q, off_r, off_p, off_d, off_b, off_xh, off_part, total;
+    size_t off_q, off_r, off_p, off_d, off_b, off_xh, off_part, off_pack, pack_bytes, total;
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -35,6 +35,8 @@ static CgLayout cg_layout(const scd_geom *g, int batch)
     L.off_b = o;  o += align256(L.img * batch * 4);    // rhs of the fused step
     L.off_xh = o; o += align256(L.img * batch * 4);    // CG iterate of the fused step
     L.off_part = o; o += align256(3 * L.part_stride * batch * 4);
+    L.pack_bytes = scd_fp_scratch_need(g, batch);
+    L.off_pack = o; o += align256(L.pack_bytes);
     L.total = o;
     return L;
 }
@@ -61,6 +63,7 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     float *q = (float *)(w + L.off_q), *r = (float *)(w + L.off_r);
     float *p = (float *)(w + L.off_p), *d = (float *)(w + L.off_d);
     float *part = (float *)(w + L.off_part);
+    void *pack = (void *)(w + L.off_pack);
     const int ps = (int)L.part_stride;
     float *rr_a = part, *rr_b = part + (size_t)ps * batch, *pd = part + 2 * (size_t)ps * batch;
     const int nbp = scd_bp_ctas_per_sample(g, batch);
@@ -69,7 +72,7 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     int rc;
 
     // r = rhs - x - gamma A*(A x);  p = r;  rr = ||r||^2
-    if ((rc = scd_launch_fp(g, x_in, q, batch, 0, g->n_angles, st))) return rc;
+    if ((rc = scd_launch_fp(g, x_in, q, batch, 0, g->n_angles, pack, L.pack_bytes, st))) return rc;
     BpEpilogue e0;
     e0.c_acc = -gs; e0.add1 = x_in; e0.c1 = -1.f; e0.add2 = rhs; e0.c2 = 1.f;
     e0.out2 = p; e0.dot_part = rr_a; e0.dot_stride = ps; e0.dot_with_add1 = 0;
@@ -79,7 +82,7 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
 
     for (int it = 0; it < n_iter; ++it) {
         // d = p + gamma A*(A p);  pd = <p,d>
-        if ((rc = scd_launch_fp(g, p, q, batch, 0, g->n_angles, st))) return rc;
+        if ((rc = scd_launch_fp(g, p, q, batch, 0, g->n_angles, pack, L.pack_bytes, st))) return rc;
         BpEpilogue e1;
         e1.c_acc = gs; e1.add1 = p; e1.c1 = 1.f; e1.add2 = nullptr; e1.c2 = 0.f;
         e1.out2 = nullptr; e1.dot_part = pd; e1.dot_stride = ps; e1.dot_with_add1 = 1;
@@ -105,10 +108,15 @@ extern "C" int scd_cg(const scd_geom_t *g, float *x, const float *rhs, double ga
     return scd_cg_run(g, x, x, rhs, (float)gamma, n_iter, batch, work, work_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
-                      int angle_lo, int angle_hi, void *stream)
+extern "C" size_t scd_fp_scratch_bytes(const scd_geom_t *g, int batch)
 {
-    return scd_launch_fp(g, img, sino, batch, angle_lo, angle_hi, (cudaStream_t)stream);
+    return scd_fp_scratch_need(g, batch);
+}
+
+extern "C" int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
+                      int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, void *stream)
+{
+    return scd_launch_fp(g, img, sino, batch, angle_lo, angle_hi, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int scd_bp(const scd_geom_t *g, const float *sino, float *out, int batch,
@@ -182,6 +190,8 @@ static int host_roundtrip(const scd_geom_t *g, const float *in_host, size_t in_e
     if (!g || !in_host || !out_host) { scd_set_error("scd_*_host: null argument"); return SCD_E_INVALID; }
     if (batch <= 0) return 0;
     float *d_in = nullptr, *d_out = nullptr;
+    void *d_scr = nullptr;
+    const size_t scr_bytes = forward ? scd_fp_scratch_need(g, batch) : 0;
     cudaStream_t st = nullptr;
     int rc = 0;
     cudaError_t e;
@@ -189,7 +199,8 @@ static int host_roundtrip(const scd_geom_t *g, const float *in_host, size_t in_e
     if ((e = cudaMalloc(&d_in, in_elems * 4)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
     if ((e = cudaMalloc(&d_out, out_elems * 4)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
     if ((e = cudaMemcpyAsync(d_in, in_host, in_elems * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = scd_cuda_fail(e, "H2D"); goto done; }
-    if (forward) rc = scd_fp(g, d_in, d_out, batch, 0, g->n_angles, st);
+    if (forward && (e = cudaMalloc(&d_scr, scr_bytes)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
+    if (forward) rc = scd_fp(g, d_in, d_out, batch, 0, g->n_angles, d_scr, scr_bytes, st);
     else rc = scd_bp(g, d_in, d_out, batch, 0, g->n_angles, (float)g->adj_scale, nullptr, 0.f, st);
     if (rc) goto done;
     if ((e = cudaMemcpyAsync(out_host, d_out, out_elems * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = scd_cuda_fail(e, "D2H"); goto done; }
@@ -197,6 +208,7 @@ static int host_roundtrip(const scd_geom_t *g, const float *in_host, size_t in_e
 done:
     if (d_in) cudaFree(d_in);
     if (d_out) cudaFree(d_out);
+    if (d_scr) cudaFree(d_scr);
     if (st) cudaStreamDestroy(st);
     return rc;
 }

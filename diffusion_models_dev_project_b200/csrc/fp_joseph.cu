@@ -25,13 +25,32 @@
 
 struct FpRun { int cls, first, count, cta0; };
 
+// Packed image ("tile-ready") layout written by fp_pack_kernel and consumed by the
+// march kernel with plain byte copies:
+//   packed[group][cls][row][col][s]      s < S samples interleaved per pixel
+//   cls 0: row = k0, col = k1            cls 1: row = k1, col = k0 (transposed)
+//   each row has `pitch` = ncols + 3 pixels: 1 zero pad left, 2 right; rows are padded
+//   with zero rows up to a multiple of TR, so a strip of TR rows is one contiguous,
+//   16-byte aligned range = exactly the shared-memory tile.
+struct FpLayout {
+    int S, TR;
+    int pitch[2];            // pixels per packed row, per class
+    int rows[2];             // packed rows per class (multiple of TR)
+    size_t cls_off[2];       // float offset of class c inside a group
+    size_t group_floats;     // floats per sample group
+};
+
 struct FpParams {
     const float   *img;
     float         *sino;
+    float         *packed;
     const FpAngle *fp;
     const int     *order;
     int n0, n1, n_angles, n_det, batch;
-    int NA, TR, pitch;
+    int NA;                 // angles per CTA
+    int G;                  // threads per angle group (multiple of 32)
+    int nbuf;               // strips in flight (shared-memory ring depth)
+    FpLayout L;
     int n_runs;
     FpRun runs[8];
 };
@@ -39,13 +58,121 @@ struct FpParams {
 #define SCD_MAGIC      12582912.0f      /* 1.5 * 2^23: float add rounds to integer */
 #define SCD_MAGIC_BITS 0x4B400000
 
-template <int S, int RPT>
+struct __align__(16) FpAngSmem { double a, b, c; float scale; int id; };
+
+// ------------------------------------------------------------------ pack ---
+// grid = (col tiles of 32, row tiles of 32 [over the padded row count], groups*2 classes)
+template <int S>
+__global__ void __launch_bounds__(256)
+fp_pack_kernel(const FpParams P)
+{
+    __shared__ float tr[S][32][33];
+    const int cls = blockIdx.z & 1, grp = blockIdx.z >> 1;
+    const int nrows = cls == 0 ? P.n0 : P.n1, ncols = cls == 0 ? P.n1 : P.n0;
+    const int pitch = P.L.pitch[cls], prow = P.L.rows[cls];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
+    const int R0 = blockIdx.y * 32, C0 = blockIdx.x * 32;
+    if (R0 >= prow || C0 >= ncols) return;
+    float *dst = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[cls];
+    const size_t isz = (size_t)P.n0 * P.n1;
+
+    if (cls == 1) {
+        // transposed orientation: load [k0 = C0.., k1 = R0..] coalesced along k1, swap via smem
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int b = grp * S + s;
+            for (int i = ty; i < 32; i += 8) {
+                const int k0 = C0 + i, k1 = R0 + tx;
+                tr[s][i][tx] = (b < P.batch && k0 < P.n0 && k1 < P.n1) ? __ldg(P.img + b * isz + (size_t)k0 * P.n1 + k1) : 0.f;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = ty; i < 32; i += 8) {
+        const int r = R0 + i, c = C0 + tx;
+        if (r >= prow) break;
+        float v[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const int b = grp * S + s;
+            if (cls == 0)
+                v[s] = (b < P.batch && r < nrows && c < ncols) ? __ldg(P.img + b * isz + (size_t)r * P.n1 + c) : 0.f;
+            else
+                v[s] = tr[s][tx][i];           // (k0 = C0 + tx = c, k1 = R0 + i = r)
+        }
+        float *q = dst + ((size_t)r * pitch + 1 + c) * S;
+        if (c < ncols) {
+            if (S == 4) *reinterpret_cast<float4 *>(q) = make_float4(v[0], v[1], v[2], v[3]);
+            else if (S == 2) *reinterpret_cast<float2 *>(q) = make_float2(v[0], v[1]);
+            else q[0] = v[0];
+        }
+        // zero pads: left pad by the first column tile, right pads by the tile holding the last column
+        if (c == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) q[s - S] = 0.f;
+        }
+        if (c == ncols - 1) {
+#pragma unroll
+            for (int s = 0; s < 2 * S; ++s) q[S + s] = 0.f;
+        }
+    }
+}
+
+// ----------------------------------------------------------------- march ---
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int S> struct VecS;
+template <> struct VecS<1> { typedef float  T; };
+template <> struct VecS<2> { typedef float2 T; };
+template <> struct VecS<4> { typedef float4 T; };
+
+__device__ __forceinline__ void tap_acc(float (&p)[1], float l, float r, float wl, float w)
+{ p[0] = fmaf(r, w, fmaf(l, wl, p[0])); }
+__device__ __forceinline__ void tap_acc(float (&p)[2], float2 l, float2 r, float wl, float w)
+{ p[0] = fmaf(r.x, w, fmaf(l.x, wl, p[0])); p[1] = fmaf(r.y, w, fmaf(l.y, wl, p[1])); }
+__device__ __forceinline__ void tap_acc(float (&p)[4], float4 l, float4 r, float wl, float w)
+{
+    p[0] = fmaf(r.x, w, fmaf(l.x, wl, p[0])); p[1] = fmaf(r.y, w, fmaf(l.y, wl, p[1]));
+    p[2] = fmaf(r.z, w, fmaf(l.z, wl, p[2])); p[3] = fmaf(r.w, w, fmaf(l.w, wl, p[3]));
+}
+
+// S  = samples marched together by one thread (interleaved per pixel: one LDS.(32*S) per tap)
+// TR = marching rows per shared-memory strip
+#define FP_MAX_NBUF 8
+template <int S, int TR>
 __global__ void __launch_bounds__(512)
 fp_joseph_kernel(const FpParams P)
 {
-    extern __shared__ float tile[];           // [S][TR][pitch]
+    typedef typename VecS<S>::T V;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
 
     // locate this CTA's run without indexing the parameter array dynamically
     FpRun R = P.runs[0];
@@ -54,180 +181,228 @@ fp_joseph_kernel(const FpParams P)
         if (k < P.n_runs && (int)blockIdx.x >= P.runs[k].cta0) R = P.runs[k];
     const int pos0 = R.first + ((int)blockIdx.x - R.cta0) * P.NA;
     const int na = min(P.NA, R.first + R.count - pos0);
-    // cls < 0: unsorted fallback (one angle per CTA, positions are angle ids)
-    const int cls = R.cls < 0 ? P.fp[pos0].cls : R.cls;
+    const int cls = R.cls;
     const int nrows = cls == 0 ? P.n0 : P.n1;   // marching axis
     const int ncols = cls == 0 ? P.n1 : P.n0;   // interpolation axis
+    const int pitch = P.L.pitch[cls];
+    const int n_det = P.n_det;
     const int b0 = blockIdx.y * S;
-    const int TR = P.TR, pitch = P.pitch;
-    const int plane = TR * pitch;
+    const unsigned strip_bytes = (unsigned)(TR * pitch * S * 4);
 
-    // ---- per-ray setup (fp64 for the affine start position) ---------------
-    const int nrays = na * P.n_det;
-    float u0[RPT], bb[RPT], sc[RPT], acc[RPT][S];
-    int   oidx[RPT];
-#pragma unroll
-    for (int m = 0; m < RPT; ++m) {
-        const int ray = tid + m * nthr;
-        u0[m] = -1.0e30f; bb[m] = 0.f; sc[m] = 0.f; oidx[m] = -1;
-        if (ray < nrays) {
-            const int ai = ray / P.n_det;
-            const int j = ray - ai * P.n_det;
-            const int ang = R.cls < 0 ? pos0 + ai : P.order[pos0 + ai];
-            const FpAngle f = P.fp[ang];
-            // z' = u + 1 (left pad column) - 0.5 (round-to-nearest == floor)
-            u0[m] = (float)(f.a * (double)j + f.c + 0.5);
-            bb[m] = (float)f.b;
-            sc[m] = f.scale;
-            oidx[m] = ang * P.n_det + j;
-        }
-#pragma unroll
-        for (int s = 0; s < S; ++s) acc[m][s] = 0.f;
+    // shared memory: tile[nbuf] | mbarriers | angle table | u0[NA*n_det] | acc[NA*n_det][S]
+    const int NBUF = P.nbuf;
+    unsigned char *tile0 = smem_raw;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + NBUF * (size_t)strip_bytes);
+    FpAngSmem *ang = reinterpret_cast<FpAngSmem *>(bars + FP_MAX_NBUF);
+    float *u0s = reinterpret_cast<float *>(ang + P.NA);
+    float *acc = u0s + ((P.NA * n_det + 3) & ~3);
+
+    const float *src = P.packed + (size_t)blockIdx.y * P.L.group_floats + P.L.cls_off[cls];
+    const int nstrips = (nrows + TR - 1) / TR;
+
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        for (int i = 0; i < NBUF; ++i)
+            if (i < nstrips) {
+                mbar_expect_tx(&bars[i], strip_bytes);
+                bulk_g2s(tile0 + (size_t)i * strip_bytes, src + (size_t)i * TR * pitch * S, strip_bytes, &bars[i]);
+            }
     }
-
-    // ---- zero the pad columns once ----------------------------------------
-    for (int row = tid; row < S * TR; row += nthr) {
-        float *q = tile + row * pitch;
-        q[0] = 0.f;
-        for (int c = ncols + 1; c < pitch; ++c) q[c] = 0.f;
+    for (int i = tid; i < na; i += nthr) {
+        const int id = P.order[pos0 + i];
+        const FpAngle f = P.fp[id];
+        FpAngSmem a;
+        a.a = f.a; a.b = f.b;
+        a.c = f.c + 1.0;                 // zf = u + 1 (left pad pixel); floor(zf) = pixel of the left tap
+        a.scale = f.scale; a.id = id;
+        ang[i] = a;
     }
-
-    const float zlim = (float)ncols + 0.5f;
-    for (int r0 = 0; r0 < nrows; r0 += TR) {
-        __syncthreads();                       // previous strip fully consumed
-        // ---- fill the strip ------------------------------------------------
+    __syncthreads();
+    for (int e = tid; e < na * n_det; e += nthr) {
+        const int ai = e / n_det, j = e - ai * n_det;
+        u0s[e] = (float)(ang[ai].a * (double)j + ang[ai].c);
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int b = b0 + s;
-            const bool bok = b < P.batch;
-            const float *src = P.img + (size_t)(bok ? b : 0) * P.n0 * P.n1;
-            float *dst = tile + s * plane + 1;
-            if (cls == 0) {
-                // tile row rr <- image row r0+rr (contiguous): coalesced both sides
-                for (int rr = warp; rr < TR; rr += nwarps) {
-                    const int r = r0 + rr;
-                    const bool ok = bok && r < nrows;
-                    const float *g = src + (size_t)(ok ? r : 0) * P.n1;
-                    float *d = dst + rr * pitch;
-#pragma unroll 4
-                    for (int c = lane; c < ncols; c += 32)
-                        d[c] = ok ? __ldg(g + c) : 0.f;
+        for (int s = 0; s < S; ++s) acc[(size_t)e * S + s] = 0.f;
+    }
+    __syncthreads();                              // mbarrier init + tables visible
+
+    const int G = P.G;
+    const int grp = tid / G, gl = tid - grp * G, ngrp = nthr / G;
+    const float zmax = (float)(ncols + 1);        // u = ncols: both taps on the right pads
+    const float zmin = 0.0f;                      // u = -1:    left tap on the left pad, weight of the right tap 0
+
+    for (int st = 0; st < nstrips; ++st) {
+        const int bi = st % NBUF;
+        mbar_wait(&bars[bi], (unsigned)((st / NBUF) & 1));
+        const unsigned char *buf = tile0 + (size_t)bi * strip_bytes;
+        const float r0f = (float)(st * TR);
+        for (int ai = grp; ai < na; ai += ngrp) {
+            const float bf = (float)ang[ai].b;
+            const float bspan = bf * (float)(TR - 1);
+            for (int j0 = 0; j0 < n_det; j0 += G) {
+                const int j = j0 + gl;
+                const bool live = j < n_det;
+                const int e = ai * n_det + (live ? j : n_det - 1);
+                const float z0 = fmaf(r0f, bf, u0s[e]);
+                // whole warp outside the image for every row of this strip -> nothing to add
+                const float za = z0, zb = z0 + bspan;
+                const bool outside = !live || fmaxf(za, zb) <= zmin || fminf(za, zb) >= zmax;
+                if (__all_sync(0xffffffffu, outside)) continue;
+                float part[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) part[s] = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < TR; ++rr) {
+                    // clamped position: outside the image both taps land on zero pad pixels
+                    const float z = fminf(fmaxf(fmaf((float)rr, bf, z0), zmin), zmax);
+                    const float t = __fadd_rd(z, SCD_MAGIC);           // floor(z) in the mantissa
+                    const float w = z - (t - SCD_MAGIC);
+                    const float wl = 1.0f - w;
+                    const V *q = reinterpret_cast<const V *>(buf + (size_t)rr * pitch * S * 4) +
+                                 (__float_as_int(t) - SCD_MAGIC_BITS);
+                    tap_acc(part, q[0], q[1], wl, w);
                 }
-            } else {
-                // transposed: tile row rr <- image column r0+rr.  Lanes run along
-                // rr (global-contiguous k1); smem stride = pitch (odd) -> no conflicts.
-                const int lpr = TR < 32 ? TR : 32;       // lanes along rr
-                const int cpw = 32 / lpr;                // columns per warp pass
-                const int lr = lane % lpr, lc = lane / lpr;
-                for (int c = warp * cpw + lc; c < ncols; c += nwarps * cpw) {
-                    const float *g = src + (size_t)c * P.n1 + r0;
-#pragma unroll 2
-                    for (int rr = lr; rr < TR; rr += lpr) {
-                        const bool ok = bok && (r0 + rr) < nrows;
-                        dst[rr * pitch + c] = ok ? __ldg(g + rr) : 0.f;
-                    }
+                if (live) {
+                    float *ap = acc + (size_t)e * S;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) ap[s] += part[s];
                 }
             }
         }
-        __syncthreads();
-
-        // ---- march ---------------------------------------------------------
-        const float r0f = (float)r0;
-#pragma unroll
-        for (int m = 0; m < RPT; ++m) {
-            if (oidx[m] < 0) continue;
-            const float bm = bb[m];
-            const float z0 = fmaf(r0f, bm, u0[m]);
-#pragma unroll 8
-            for (int rr = 0; rr < TR; ++rr) {
-                const float z = fmaf((float)rr, bm, z0);
-                const float t = z + SCD_MAGIC;
-                const float kf = t - SCD_MAGIC;
-                const float w = (z - kf) + 0.5f;
-                const int k = __float_as_int(t) - SCD_MAGIC_BITS;
-                if (z >= -0.5f && z < zlim) {
-                    const float *q = tile + rr * pitch + k;
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        const float f0 = q[s * plane];
-                        const float f1 = q[s * plane + 1];
-                        acc[m][s] += fmaf(w, f1 - f0, f0);
-                    }
-                }
-            }
+        __syncthreads();                          // every thread is done with buffer bi
+        if (tid == 0 && st + NBUF < nstrips) {
+            mbar_expect_tx(&bars[bi], strip_bytes);
+            bulk_g2s(tile0 + (size_t)bi * strip_bytes, src + (size_t)(st + NBUF) * TR * pitch * S, strip_bytes, &bars[bi]);
         }
     }
 
-    // ---- write the line integrals -----------------------------------------
-    const size_t sino_sz = (size_t)P.n_angles * P.n_det;
+    // ---- write the line integrals (coalesced along the detector) ----------
+    const size_t sino_sz = (size_t)P.n_angles * n_det;
+    for (int e = tid; e < na * n_det; e += nthr) {
+        const int ai = e / n_det, j = e - ai * n_det;
+        const float sc = ang[ai].scale;
+        const size_t o = (size_t)ang[ai].id * n_det + j;
 #pragma unroll
-    for (int m = 0; m < RPT; ++m) {
-        if (oidx[m] < 0) continue;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int b = b0 + s;
-            if (b < P.batch) P.sino[(size_t)b * sino_sz + oidx[m]] = acc[m][s] * sc[m];
-        }
+        for (int s = 0; s < S; ++s)
+            if (b0 + s < P.batch) P.sino[(size_t)(b0 + s) * sino_sz + o] = acc[(size_t)e * S + s] * sc;
     }
 }
 
 // ------------------------------------------------------------- host side ---
-struct FpConfig { int S, RPT, NA, TR, threads, pitch; size_t smem; };
+struct FpConfig { int S, TR, NA, G, threads, nbuf; FpLayout L; size_t smem; int groups; size_t scratch_bytes; };
+
+static FpLayout fp_layout(const scd_geom *g, int S, int TR)
+{
+    FpLayout L;
+    L.S = S; L.TR = TR;
+    const int nr[2] = {g->n0, g->n1}, nc[2] = {g->n1, g->n0};
+    size_t off = 0;
+    for (int c = 0; c < 2; ++c) {
+        L.pitch[c] = nc[c] + 3;
+        L.rows[c] = ((nr[c] + TR - 1) / TR) * TR;
+        L.cls_off[c] = off;
+        off += (size_t)L.rows[c] * L.pitch[c] * S;
+        off = (off + 31) & ~(size_t)31;            // keep every class 128-byte aligned
+    }
+    L.group_floats = off;
+    return L;
+}
+
+static size_t fp_smem_bytes(const scd_geom *g, const FpConfig &c)
+{
+    const size_t strip = (size_t)c.TR * std::max(c.L.pitch[0], c.L.pitch[1]) * c.S * 4;
+    const size_t nray = ((size_t)c.NA * g->n_det + 3) & ~(size_t)3;
+    return c.nbuf * strip + FP_MAX_NBUF * 8 + sizeof(FpAngSmem) * c.NA + 4 * nray + 4 * nray * c.S + 16;
+}
 
 static FpConfig fp_choose(const scd_geom *g, int batch, int n_sel_angles)
 {
     FpConfig c;
-    const int nmax = std::max(g->n0, g->n1);
-    c.pitch = nmax + 2;
-    if ((c.pitch & 1) == 0) c.pitch += 1;
-    // samples per thread: amortise the index arithmetic when the batch is large
-    c.S = batch >= 64 ? 4 : (batch >= 16 ? 2 : 1);
+    // Large batches: 4 samples per thread (one LDS.128 per tap), 5 angles per CTA and 8-row
+    // strips keep two 512-thread CTAs per SM (~103 KB each at 256x256).  Small batches trade
+    // that efficiency for CTAs: one angle and fewer samples per CTA.
+    c.S = batch >= 32 ? 4 : (batch >= 4 ? 2 : 1);
     if (g->tune_fp_samples) c.S = g->tune_fp_samples;
-    c.NA = g->tune_fp_angles ? g->tune_fp_angles : 2;
+    if (c.S != 1 && c.S != 2 && c.S != 4) c.S = 1;
+    c.groups = (batch + c.S - 1) / c.S;
+    const int n_cta_angles = n_sel_angles;
+    // One angle per CTA measured fastest at every batch size on B200 (more, smaller CTAs; the
+    // packed strips are re-read from L2, which sustains it); larger chunks remain selectable.
+    int na = 1;
+    (void)n_cta_angles;
+    c.NA = g->tune_fp_angles ? g->tune_fp_angles : na;
     c.NA = std::max(1, std::min(c.NA, n_sel_angles));
-    c.TR = g->tune_fp_rows ? g->tune_fp_rows : 32;
-    // keep the tile inside the opt-in shared memory limit
-    while ((size_t)c.S * c.TR * c.pitch * 4 > (size_t)g->smem_optin && c.TR > 8) c.TR >>= 1;
-    while ((size_t)c.S * c.TR * c.pitch * 4 > (size_t)g->smem_optin && c.S > 1) c.S >>= 1;
-    // threads own RPT <= 4 rays each; at most 512 threads per CTA
-    int want = g->tune_fp_threads ? g->tune_fp_threads : 384;
-    want = std::max(64, std::min(want, 512));
-    while (c.NA > 1 && c.NA * g->n_det > 4 * 512) --c.NA;
-    const int nrays = c.NA * g->n_det;
-    c.RPT = 1;
-    while (c.RPT < 4 && (nrays + c.RPT - 1) / c.RPT > want) c.RPT <<= 1;
-    int thr = (nrays + c.RPT - 1) / c.RPT;
-    thr = ((thr + 31) / 32) * 32;
-    c.threads = std::max(thr, 64);
-    c.smem = (size_t)c.S * c.TR * c.pitch * 4;
+    c.TR = g->tune_fp_rows ? g->tune_fp_rows : (c.S == 4 ? 8 : 16);
+    if (c.TR != 8 && c.TR != 16 && c.TR != 32) c.TR = 16;
+    c.G = 128;
+    int thr = g->tune_fp_threads ? g->tune_fp_threads : (c.NA >= 4 ? 512 : 384);
+    if (c.NA == 1) c.G = ((std::min(thr, g->n_det) + 31) / 32) * 32;   // one group spans the detector
+    thr = std::max(c.G, (thr / c.G) * c.G);
+    c.threads = std::min(thr, 512);
+    if (c.threads < c.G) c.G = c.threads;
+    // ring depth: with few rays per CTA a strip is consumed faster than a bulk copy lands, so
+    // keep several strips in flight; budget ~100 KB (2 CTAs/SM), whole opt-in smem if the grid
+    // has at most one CTA per SM anyway
+    c.nbuf = 2;
+    for (;;) {
+        c.L = fp_layout(g, c.S, c.TR);
+        c.smem = fp_smem_bytes(g, c);
+        if (c.smem <= (size_t)g->smem_optin) break;
+        if (c.NA > 1 && (size_t)c.NA * g->n_det * (c.S + 1) * 4 > c.smem / 2) c.NA = (c.NA + 1) / 2;
+        else if (c.TR > 8) c.TR >>= 1;
+        else if (c.S > 1) c.S >>= 1;
+        else if (c.NA > 1) c.NA = (c.NA + 1) / 2;
+        else break;
+    }
+    {
+        const int nr = std::max(g->n0, g->n1);
+        const int nstrips = (nr + c.TR - 1) / c.TR;
+        const long ctas = (long)((batch + c.S - 1) / c.S) * ((n_sel_angles + c.NA - 1) / c.NA);
+        const size_t budget = ctas <= g->sm_count ? (size_t)g->smem_optin
+                              : (ctas <= 2L * g->sm_count ? (size_t)110 * 1024 : (size_t)72 * 1024);
+        int want = g->tune_fp_nbuf ? g->tune_fp_nbuf : 3;
+        want = std::max(2, std::min(std::min(want, FP_MAX_NBUF), nstrips));
+        while (c.nbuf < want) {
+            c.nbuf++;
+            if (fp_smem_bytes(g, c) > (g->tune_fp_nbuf ? (size_t)g->smem_optin : budget)) { c.nbuf--; break; }
+        }
+        c.smem = fp_smem_bytes(g, c);
+    }
+    c.groups = (batch + c.S - 1) / c.S;
+    c.scratch_bytes = (size_t)c.groups * c.L.group_floats * 4;
     return c;
 }
 
-static FpConfig fp_choose_na1(const scd_geom *g, FpConfig c)
+size_t scd_fp_scratch_need(const scd_geom *g, int batch)
 {
-    c.NA = 1;
-    c.RPT = 1;
-    while (c.RPT < 4 && (g->n_det + c.RPT - 1) / c.RPT > 512) c.RPT <<= 1;
-    c.threads = std::max(64, ((g->n_det + c.RPT - 1) / c.RPT + 31) / 32 * 32);
-    return c;
+    if (!g || batch <= 0) return 0;
+    // the configuration may be overridden by tuning: size for the worst case (S = 1 packs least densely)
+    size_t need = 0;
+    for (int S = 1; S <= 4; S <<= 1)
+        for (int TR = 8; TR <= 32; TR <<= 1) {
+            const FpLayout L = fp_layout(g, S, TR);
+            need = std::max(need, (size_t)((batch + S - 1) / S) * L.group_floats * 4);
+        }
+    return need + 256;
 }
 
-template <int S, int RPT>
+template <int S, int TR>
 static int fp_launch_t(const FpParams &P, dim3 grid, int threads, size_t smem, cudaStream_t st)
 {
     static int configured_smem = 0;     // per instantiation
     if ((int)smem > configured_smem) {
-        SCD_CUDA(cudaFuncSetAttribute(fp_joseph_kernel<S, RPT>,
+        SCD_CUDA(cudaFuncSetAttribute(fp_joseph_kernel<S, TR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_smem = (int)smem;
     }
-    fp_joseph_kernel<S, RPT><<<grid, threads, smem, st>>>(P);
+    fp_joseph_kernel<S, TR><<<grid, threads, smem, st>>>(P);
     SCD_LAUNCH_CHECK("fp_joseph_kernel");
     return 0;
 }
 
 int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
-                  int angle_lo, int angle_hi, cudaStream_t st)
+                  int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st)
 {
     if (!g || !img || !sino) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
@@ -236,49 +411,59 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
         return SCD_E_INVALID;
     }
     if (batch == 0 || angle_lo == angle_hi) return 0;
-    if (g->n_det > 2048) { scd_set_error("scd_fp: n_det > 2048 unsupported"); return SCD_E_INVALID; }
 
     FpConfig c = fp_choose(g, batch, angle_hi - angle_lo);
+    if (c.smem > (size_t)g->smem_optin) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
+    const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
+    if (!scratch || sp + c.scratch_bytes > (uintptr_t)scratch + scratch_bytes) {
+        scd_set_error("scd_fp: scratch too small (%zu bytes given, %zu needed; see scd_fp_scratch_bytes)",
+                      scratch_bytes, c.scratch_bytes + 128);
+        return SCD_E_WORKSPACE;
+    }
     FpParams P;
-    P.img = img; P.sino = sino; P.fp = g->d_fp; P.order = g->d_order;
+    P.img = img; P.sino = sino; P.packed = (float *)sp; P.fp = g->d_fp; P.order = g->d_order;
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
-    P.TR = c.TR; P.pitch = c.pitch;
+    P.NA = c.NA; P.G = c.G; P.nbuf = c.nbuf; P.L = c.L; P.n_runs = 0;
+    const unsigned gy = (unsigned)c.groups;
+    if (gy > 32767u) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
 
-    // runs of order[] positions whose angle lies in [angle_lo, angle_hi), per class
-    P.NA = c.NA;
-    P.n_runs = 0;
-    int cta = 0;
-    bool overflow = false;
+    // ---- pack: image -> tile-ready layout (both orientations) ----
+    {
+        const int maxr = std::max(c.L.rows[0], c.L.rows[1]), maxc = std::max(g->n0, g->n1);
+        dim3 pg((maxc + 31) / 32, (maxr + 31) / 32, gy * 2);
+        if (c.S == 1) fp_pack_kernel<1><<<pg, 256, 0, st>>>(P);
+        else if (c.S == 2) fp_pack_kernel<2><<<pg, 256, 0, st>>>(P);
+        else fp_pack_kernel<4><<<pg, 256, 0, st>>>(P);
+        SCD_LAUNCH_CHECK("fp_pack_kernel");
+    }
+
+    // runs of order[] positions whose angle lies in [angle_lo, angle_hi), per class; a
+    // launch takes up to 8 runs (monotone angle lists need at most 3), more runs -> more launches
     int pos = 0;
     while (pos < g->n_angles) {
-        const int a = g->h_order[pos];
-        if (a < angle_lo || a >= angle_hi) { ++pos; continue; }
-        const int cls = g->h_fp[a].cls;
-        int end = pos + 1;
-        while (end < g->n_angles && g->h_order[end] >= angle_lo && g->h_order[end] < angle_hi &&
-               g->h_fp[g->h_order[end]].cls == cls) ++end;
-        if (P.n_runs == 8) { overflow = true; break; }
-        FpRun &r = P.runs[P.n_runs++];
-        r.cls = cls; r.first = pos; r.count = end - pos; r.cta0 = cta;
-        cta += (r.count + c.NA - 1) / c.NA;
-        pos = end;
-    }
-    if (overflow) {
-        // angle list interleaves the two classes too often: one angle per CTA,
-        // class looked up per angle (cls = -1), positions are angle ids
-        c = fp_choose_na1(g, c);
-        P.NA = 1; P.n_runs = 1;
-        P.runs[0].cls = -1; P.runs[0].first = angle_lo; P.runs[0].count = angle_hi - angle_lo;
-        P.runs[0].cta0 = 0;
-        cta = angle_hi - angle_lo;
-    }
-    dim3 grid(cta, (batch + c.S - 1) / c.S);
-    if (grid.y > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
-#define FP_CASE(SS, RR) if (c.S == SS && c.RPT == RR) return fp_launch_t<SS, RR>(P, grid, c.threads, c.smem, st);
-    FP_CASE(1, 1) FP_CASE(1, 2) FP_CASE(1, 4)
-    FP_CASE(2, 1) FP_CASE(2, 2) FP_CASE(2, 4)
-    FP_CASE(4, 1) FP_CASE(4, 2) FP_CASE(4, 4)
+        P.n_runs = 0;
+        int cta = 0;
+        while (pos < g->n_angles && P.n_runs < 8) {
+            const int a = g->h_order[pos];
+            if (a < angle_lo || a >= angle_hi) { ++pos; continue; }
+            const int cls = g->h_fp[a].cls;
+            int end = pos + 1;
+            while (end < g->n_angles && g->h_order[end] >= angle_lo && g->h_order[end] < angle_hi &&
+                   g->h_fp[g->h_order[end]].cls == cls) ++end;
+            FpRun &r = P.runs[P.n_runs++];
+            r.cls = cls; r.first = pos; r.count = end - pos; r.cta0 = cta;
+            cta += (r.count + c.NA - 1) / c.NA;
+            pos = end;
+        }
+        if (P.n_runs == 0) break;
+        dim3 grid(cta, gy);
+        int rc = SCD_E_INVALID;
+#define FP_CASE(SS, TT) if (c.S == SS && c.TR == TT) rc = fp_launch_t<SS, TT>(P, grid, c.threads, c.smem, st);
+        FP_CASE(1, 8) FP_CASE(1, 16) FP_CASE(1, 32)
+        FP_CASE(2, 8) FP_CASE(2, 16) FP_CASE(2, 32)
+        FP_CASE(4, 8) FP_CASE(4, 16) FP_CASE(4, 32)
 #undef FP_CASE
-    scd_set_error("scd_fp: unsupported config S=%d RPT=%d", c.S, c.RPT);
-    return SCD_E_INVALID;
+        if (rc) return rc;
+    }
+    return 0;
 }

@@ -57,13 +57,17 @@ struct scd_geom {
     int     *h_order;
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
-    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads;
+    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf;
     int tune_bp_samples, tune_bp_tile;
 };
 
 // ------------------------------------------------------------ launchers ----
+// scratch: caller-owned device buffer of >= scd_fp_scratch_need(g, batch) bytes that
+// receives the packed ("tile-ready") copy of the image
 int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
-                  int angle_lo, int angle_hi, cudaStream_t st);
+                  int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
+                  cudaStream_t st);
+size_t scd_fp_scratch_need(const scd_geom *g, int batch);
 
 // Backprojection with fused epilogue:
 //   val  = c_acc*BP + c1*add1 + c2*add2

@@ -178,6 +178,17 @@ class B200RayTrafo(BaseRayTrafo):
             self._work[key] = w
         return w
 
+    def fp_scratch(self, batch: int, device: torch.device) -> Tensor:
+        """Scratch for scd_fp (packed copy of the images), cached per device and batch."""
+        h = self._handle(device)
+        key = ('fp', h.device.index, batch)
+        w = self._work.get(key)
+        if w is None:
+            nbytes = int(h._lib.scd_fp_scratch_bytes(h.ptr, batch))
+            w = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+            self._work[key] = w
+        return w
+
     @staticmethod
     def _aligned(w: Tensor):
         p = w.data_ptr()
@@ -195,9 +206,10 @@ class B200RayTrafo(BaseRayTrafo):
             y = torch.empty(*lead, *self.obs_shape, dtype=torch.float32, device=x.device)
         else:
             y = torch.zeros(*lead, *self.obs_shape, dtype=torch.float32, device=x.device)
+        scr = self.fp_scratch(batch, x.device)
         with torch.cuda.device(x.device):
             _lib.check(h._lib.scd_fp(h.ptr, x.data_ptr(), y.data_ptr(), batch, lo, hi,
-                                     _stream_ptr(x.device)), 'scd_fp')
+                                     scr.data_ptr(), scr.numel(), _stream_ptr(x.device)), 'scd_fp')
         return y
 
     def _bp(self, y: Tensor, scale: float, addend: Tensor = None, addend_scale: float = 0.0,

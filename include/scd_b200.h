@@ -68,9 +68,14 @@ int scd_geom_destroy(scd_geom_t *g);
 
 /* A: forward projection of angles [angle_lo, angle_hi) (rows outside that
  * range of `sino` are left untouched; sino always has n_angles rows).
+ * `scratch` is a caller-owned device buffer of at least
+ * scd_fp_scratch_bytes(g, batch) bytes: the projector first re-packs the images
+ * into the layout its shared-memory strips are bulk-copied from.
  * Replaces: SimpleTrafo.trafo -> ODL/ASTRA par_fp (src/physics/trafo.py:58). */
+size_t scd_fp_scratch_bytes(const scd_geom_t *g, int batch);
 int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
-           int angle_lo, int angle_hi, void *stream);
+           int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
+           void *stream);
 
 /* A*: out = c_acc * BP(sino; angles [lo,hi)) + c_add * addend
  * where BP is the un-scaled pixel-driven sum; the plain adjoint is
@@ -141,7 +146,7 @@ int scd_geom_info(const scd_geom_t *g, int32_t *n0, int32_t *n1,
 int64_t scd_launch_count(void);
 void    scd_launch_count_reset(void);
 /* Override launch heuristics (tuning / tests).  key is one of
- * "fp_samples", "fp_angles", "fp_rows", "bp_samples", "bp_tile"; value 0
+ * "fp_samples", "fp_angles", "fp_rows", "fp_threads", "fp_nbuf", "bp_samples", "bp_tile"; value 0
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */
 int scd_set_tuning(scd_geom_t *g, const char *key, int value);
 

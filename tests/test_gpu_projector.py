@@ -1,0 +1,193 @@
+"""GPU parity of A (fp_joseph) and A* (bp_pixel) against the CPU oracle, through the C ABI.
+
+Tolerance: 1e-4 relative L2 (BASELINE.json north_star); observed values are ~1e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _rt(im_shape, num_angles, **kw):
+    from diffusion_models_dev_project_b200 import B200RayTrafo
+    return B200RayTrafo(im_shape, num_angles, **kw)
+
+
+def _phantoms(golden, n):
+    d = golden('dds_256.npz')
+    imgs = [d['gt_0'][0, 0], d['gt_1'][0, 0]]
+    rng = np.random.default_rng(0)
+    while len(imgs) < n:
+        imgs.append(rng.random((256, 256), dtype=np.float32))
+    return np.stack(imgs[:n])[:, None]
+
+
+@pytest.mark.parametrize('batch', [1, 3, 16, 65])
+def test_fp_256_matches_oracle(golden, batch):
+    geom = O.OracleGeometry((256, 256), 60)
+    rt = _rt((256, 256), 60)
+    x = _phantoms(golden, min(batch, 4))
+    x = np.concatenate([x] * ((batch + len(x) - 1) // len(x)))[:batch]
+    x = x * np.linspace(0.5, 1.5, batch, dtype=np.float32)[:, None, None, None]
+    y = rt(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert y.shape == (batch, 1, 60, 365)
+    y_ref = O.fp(geom, x[:4])
+    assert rel_l2(y[:4], y_ref) < TOL
+    # remaining samples are scaled copies: linearity gives the check for free
+    for b in range(4, batch):
+        assert rel_l2(y[b] / np.float32(np.linspace(0.5, 1.5, batch)[b]),
+                      y[b % 4] / np.float32(np.linspace(0.5, 1.5, batch)[b % 4])) < 1e-5
+
+
+@pytest.mark.parametrize('batch', [1, 3, 16, 65])
+def test_bp_256_matches_oracle(batch):
+    geom = O.OracleGeometry((256, 256), 60)
+    rt = _rt((256, 256), 60)
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal((batch, 1, 60, 365)).astype(np.float32)
+    x = rt.trafo_adjoint(torch.from_numpy(y).cuda()).cpu().numpy()
+    assert x.shape == (batch, 1, 256, 256)
+    n = min(batch, 3)
+    assert rel_l2(x[:n], O.bp(geom, y[:n])) < TOL
+    if batch > 3:
+        assert rel_l2(x[-1], O.bp(geom, y[-1])) < TOL
+
+
+@pytest.mark.parametrize('im_shape,num_angles', [((501, 501), 24), ((48, 80), 7), ((33, 17), 5), ((128, 128), 90)])
+def test_fp_bp_other_shapes(im_shape, num_angles):
+    geom = O.OracleGeometry(im_shape, num_angles)
+    rt = _rt(im_shape, num_angles)
+    rng = np.random.default_rng(2)
+    x = rng.random((2, 1, *im_shape), dtype=np.float32)
+    y = rt(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert y.shape[-2:] == geom.obs_shape
+    assert rel_l2(y, O.fp(geom, x)) < TOL
+    g = rng.standard_normal((2, 1, *geom.obs_shape)).astype(np.float32)
+    z = rt.trafo_adjoint(torch.from_numpy(g).cuda()).cpu().numpy()
+    assert rel_l2(z, O.bp(geom, g)) < TOL
+
+
+@pytest.mark.parametrize('tune', [dict(fp_samples=1, fp_angles=1), dict(fp_samples=2, fp_angles=3, fp_rows=16),
+                                  dict(fp_samples=4, fp_angles=4, fp_rows=8), dict(fp_samples=4, fp_angles=2, fp_threads=256),
+                                  dict(bp_samples=2, bp_tile=16), dict(bp_samples=4, bp_tile=64), dict(bp_samples=1, bp_tile=32)])
+def test_tuning_variants_agree(tune):
+    """Every template instantiation (samples per thread, rays per thread, tile shape) computes the same thing."""
+    geom = O.OracleGeometry((96, 96), 20)
+    rt = _rt((96, 96), 20)
+    rt.set_tuning('cuda', **tune)
+    rng = np.random.default_rng(3)
+    x = rng.random((5, 1, 96, 96), dtype=np.float32)
+    g = rng.standard_normal((5, 1, *geom.obs_shape)).astype(np.float32)
+    assert rel_l2(rt(torch.from_numpy(x).cuda()).cpu().numpy(), O.fp(geom, x)) < TOL
+    assert rel_l2(rt.trafo_adjoint(torch.from_numpy(g).cuda()).cpu().numpy(), O.bp(geom, g)) < TOL
+
+
+def test_known_answers_disc_and_ones():
+    """Analytic line integrals: centred disc -> 2*sqrt(R^2-s^2); A*(1) = pi inside the FOV."""
+    rt = _rt((256, 256), 60)
+    geom = rt.geometry
+    k = np.arange(256) - 128 + 0.5
+    R = 80.0
+    disc = ((k[:, None] ** 2 + k[None, :] ** 2) <= R * R).astype(np.float32)
+    y = rt(torch.from_numpy(disc)[None, None].cuda()).cpu().numpy()[0, 0]
+    s = geom.s_min + (np.arange(geom.n_det) + 0.5) * geom.ds
+    exact = 2 * np.sqrt(np.clip(R * R - s * s, 0, None))
+    inner = np.abs(s) < R - 3
+    assert np.abs(y[:, inner] - exact[inner]).max() < 1.5          # pixelised disc edge
+    assert abs(y[:, inner].mean() / exact[inner].mean() - 1) < 2e-3
+    ones = torch.ones(1, 1, 60, 365).cuda()
+    bp1 = rt.trafo_adjoint(ones).cpu().numpy()
+    assert np.allclose(bp1, np.pi, rtol=1e-5)
+
+
+def test_angle_ranges_partition():
+    """Angle-sharded A / A*: the per-range results add up to the full operator (config 4)."""
+    geom = O.OracleGeometry((64, 64), 24)
+    rt = _rt((64, 64), 24)
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.random((3, 1, 64, 64), dtype=np.float32)).cuda()
+    g = torch.from_numpy(rng.standard_normal((3, 1, *geom.obs_shape)).astype(np.float32)).cuda()
+    full_y, full_x = rt(x), rt.trafo_adjoint(g)
+    parts = [(0, 5), (5, 6), (6, 19), (19, 24)]
+    acc_y = torch.zeros_like(full_y)
+    acc_x = torch.zeros_like(full_x)
+    for lo, hi in parts:
+        yp = rt._fp(x, angle_range=(lo, hi))
+        assert torch.equal(yp[..., lo:hi, :], full_y[..., lo:hi, :])
+        assert float(yp[..., :lo, :].abs().max() if lo else 0) == 0
+        acc_y += yp
+        xp = rt._bp(g, rt.adj_scale, angle_range=(lo, hi))
+        assert rel_l2(xp.cpu().numpy(), O.bp(geom, g.cpu().numpy(), angle_range=(lo, hi))) < TOL
+        acc_x += xp
+    assert torch.equal(acc_y, full_y)
+    assert rel_l2(acc_x.cpu().numpy(), full_x.cpu().numpy()) < 1e-6
+
+
+def test_linearity_and_dot_product_full_size():
+    """Size-independent properties at the bench size (batch 8): linearity, and <Ax,y> vs <x,A*y>."""
+    rt = _rt((256, 256), 60)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    x1 = torch.rand(8, 1, 256, 256, device='cuda', generator=gen)
+    x2 = torch.rand(8, 1, 256, 256, device='cuda', generator=gen)
+    y = torch.randn(8, 1, 60, 365, device='cuda', generator=gen)
+    lin = rt(2 * x1 - 3 * x2) - (2 * rt(x1) - 3 * rt(x2))
+    assert float(lin.norm() / rt(x1).norm()) < 1e-5
+    # A* is the pixel-driven backprojector, not the exact transpose: the weighted inner
+    # products agree to the matched/unmatched gap (~1e-2), not to round-off
+    c_w = rt.geometry.range_weight
+    lhs = (rt(x1).double() * y.double()).sum().item() * c_w
+    rhs = (x1.double() * rt.trafo_adjoint(y).double()).sum().item()
+    assert abs(lhs - rhs) / abs(rhs) < 0.05
+    # with a smooth sinogram the two adjoints agree closely
+    ys = rt(x2)
+    lhs = (rt(x1).double() * ys.double()).sum().item() * c_w
+    rhs = (x1.double() * rt.trafo_adjoint(ys).double()).sum().item()
+    assert abs(lhs - rhs) / abs(rhs) < 2e-3
+
+
+def test_flat_interface_and_shapes():
+    rt = _rt((64, 64), 10)
+    x = torch.rand(2, 3, 64, 64, device='cuda')
+    y = rt(x)
+    assert y.shape == (2, 3, 10, rt.obs_shape[1])
+    yf = rt.trafo_flat(x.reshape(6, -1).T)
+    assert yf.shape == (10 * rt.obs_shape[1], 6)
+    assert torch.equal(yf.T.reshape(2, 3, 10, -1), y)
+    xf = rt.trafo_adjoint_flat(yf)
+    assert torch.equal(xf.T.reshape(2, 3, 64, 64), rt.trafo_adjoint(y))
+    assert not hasattr(rt, 'resize')
+    assert rt.angles.shape == (10,)
+
+
+def test_errors_are_loud():
+    rt = _rt((64, 64), 10)
+    with pytest.raises(RuntimeError):
+        rt(torch.rand(1, 1, 64, 64))                      # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        rt(torch.rand(1, 1, 64, 64, device='cuda', dtype=torch.float64))
+    with pytest.raises(ValueError):
+        rt(torch.rand(1, 1, 32, 64, device='cuda'))
+    with pytest.raises(ValueError):
+        rt.trafo_adjoint(torch.rand(1, 1, 10, 7, device='cuda'))
+
+
+def test_host_buffer_entry_points():
+    import ctypes as C
+    from diffusion_models_dev_project_b200 import _lib
+    geom = O.OracleGeometry((64, 64), 10)
+    rt = _rt((64, 64), 10)
+    h = rt._handle(torch.device('cuda'))
+    x = np.random.default_rng(5).random((2, 64, 64), dtype=np.float32)
+    y = np.empty((2, *geom.obs_shape), dtype=np.float32)
+    _lib.check(h._lib.scd_fp_host(h.ptr, x.ctypes.data, y.ctypes.data, 2), 'scd_fp_host')
+    assert rel_l2(y, O.fp(geom, x)) < TOL
+    z = np.empty_like(x)
+    _lib.check(h._lib.scd_bp_host(h.ptr, y.ctypes.data, z.ctypes.data, 2), 'scd_bp_host')
+    assert rel_l2(z, O.bp(geom, y)) < TOL
+    assert h._lib.scd_fp(h.ptr, None, None, 1, 0, 10, None, 0, None) == _lib.SCD_E_INVALID
+    assert 'null' in _lib.last_error()
