@@ -25,7 +25,7 @@ static CgLayout cg_layout(const scd_geom *g, int batch)
     L.img = (size_t)g->n0 * g->n1;
     L.sino = (size_t)g->n_angles * g->n_det;
     const int nbp = scd_bp_ctas_per_sample(g, batch);
-    const int nvec = scd_vec_blocks_per_sample((int64_t)L.img);
+    const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
     L.part_stride = (size_t)std::max(nbp, nvec);
     size_t o = 0;
     L.off_q = o;  o += align256(L.sino * batch * 4);
@@ -67,7 +67,7 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     const int ps = (int)L.part_stride;
     float *rr_a = part, *rr_b = part + (size_t)ps * batch, *pd = part + 2 * (size_t)ps * batch;
     const int nbp = scd_bp_ctas_per_sample(g, batch);
-    const int nvec = scd_vec_blocks_per_sample((int64_t)L.img);
+    const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
     const float gs = gamma * (float)g->adj_scale;
     int rc;
 

@@ -90,7 +90,7 @@ int scd_bp_ctas_per_sample(const scd_geom *g, int batch);
 // Vector kernels of the CG recurrences (vec_ops.cu).  *_part arrays hold
 // per-block partial sums [batch][part_stride]; consumers add them in index
 // order (deterministic, no atomics).
-int scd_vec_blocks_per_sample(int64_t numel);
+int scd_vec_blocks_per_sample(int64_t numel, int batch);
 int scd_launch_cg_update_xr(const float *x_in, float *x, float *r, const float *p, const float *d,
                             const float *rr_part, int rr_n,
                             const float *pd_part, int pd_n, int part_stride,

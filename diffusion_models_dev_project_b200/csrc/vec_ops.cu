@@ -22,9 +22,13 @@
 
 #define VEC_THREADS 256
 
-int scd_vec_blocks_per_sample(int64_t numel)
+int scd_vec_blocks_per_sample(int64_t numel, int batch)
 {
-    int64_t nb = (numel + 4095) / 4096;      // ~16 elements per thread
+    // >= ~4 CTAs per SM over the whole batch (148 SMs), at least one float4 per thread,
+    // at most 64 blocks per sample (the consumers sum the per-block partials serially)
+    int64_t nb = (4 * 148 + batch - 1) / (batch > 0 ? batch : 1);
+    const int64_t cap = (numel + 4 * VEC_THREADS - 1) / (4 * VEC_THREADS);
+    if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     if (nb > 64) nb = 64;
     return (int)nb;
@@ -267,7 +271,7 @@ int scd_launch_cg_update_xr(const float *x_in, float *x, float *r, const float *
                             cudaStream_t st)
 {
     if (batch <= 0 || numel <= 0) return 0;
-    dim3 grid(scd_vec_blocks_per_sample(numel), batch);
+    dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, x, r, p, d, x_in))
         cg_update_xr_kernel<true><<<grid, VEC_THREADS, 0, st>>>(x_in, x, r, p, d, rr_part, rr_n, pd_part, pd_n,
                                                                part_stride, rr_new_part, numel);
@@ -283,7 +287,7 @@ int scd_launch_cg_update_p(float *p, const float *r, const float *rr_new_part, i
                            int64_t numel, cudaStream_t st)
 {
     if (batch <= 0 || numel <= 0) return 0;
-    dim3 grid(scd_vec_blocks_per_sample(numel), batch);
+    dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, p, r))
         cg_update_p_kernel<true><<<grid, VEC_THREADS, 0, st>>>(p, r, rr_new_part, rr_new_n, rr_old_part,
                                                               rr_old_n, part_stride, numel);
@@ -299,7 +303,7 @@ int scd_launch_tweedie_rhs(const float *x, const float *s, const float *atb, con
                            int batch, int64_t numel, cudaStream_t st)
 {
     if (batch <= 0 || numel <= 0) return 0;
-    dim3 grid(scd_vec_blocks_per_sample(numel), batch);
+    dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, x, s, atb, xhat0, b))
         tweedie_rhs_kernel<true><<<grid, VEC_THREADS, 0, st>>>(x, s, atb, t, abar, n_table, gamma, xhat0, b, numel);
     else
@@ -313,7 +317,7 @@ int scd_launch_ddim(const float *xhat, const float *s, const float *eps, const f
                     float *out, int batch, int64_t numel, cudaStream_t st)
 {
     if (batch <= 0 || numel <= 0) return 0;
-    dim3 grid(scd_vec_blocks_per_sample(numel), batch);
+    dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, xhat, s, eps, out))
         ddim_kernel<true><<<grid, VEC_THREADS, 0, st>>>(xhat, s, eps, t, t_prev, abar, n_table, eta, eta2, out, numel);
     else

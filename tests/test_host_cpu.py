@@ -1,0 +1,280 @@
+"""CPU tests of the host-side mirror of the reference interfaces and of the C-ABI library
+(loads, exports every declared symbol, rejects use without a GPU -- no compute calls here)."""
+import functools
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, rel_l2
+from oracle import oracle as O
+
+import diffusion_models_dev_project_b200 as pkg
+from diffusion_models_dev_project_b200 import _lib
+
+
+# ------------------------------------------------------------------ C ABI ----
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'scd_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(scd_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), 'libscd_b200.so does not export %s' % n
+        assert n in _lib.SIGNATURES, 'python binding missing for %s' % n
+    assert set(_lib.SIGNATURES) == set(names)
+    assert b'sm_100a' in lib.scd_version()
+
+
+def test_library_contains_sm100a_code_with_bulk_copies():
+    import shutil
+    import subprocess
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not available')
+    out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'UBLKCP' in sass          # cp.async.bulk (TMA unit) feeding fp_joseph
+    assert 'SYNCS' in sass           # mbarrier
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the behaviour without a GPU')
+def test_no_cpu_fallback():
+    rt = pkg.B200RayTrafo((32, 32), 6)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        rt(torch.rand(1, 1, 32, 32))
+    with pytest.raises(RuntimeError):
+        rt.trafo_adjoint(torch.rand(1, 1, *rt.obs_shape))
+    import ctypes as C
+    lib = _lib.load()
+    ang = np.array([0.1, 0.2])
+    desc = _lib.GeomDesc(n0=8, n1=8, x_min=-4, y_min=-4, dx=1, n_angles=2,
+                         angles=ang.ctypes.data_as(C.POINTER(C.c_double)), n_det=13, s_min=-6, ds=1, adj_scale=1)
+    h = C.c_void_p()
+    assert lib.scd_geom_create(C.byref(desc), C.byref(h)) == _lib.SCD_E_NODEVICE
+    assert 'no CPU path' in _lib.last_error() or 'CUDA' in _lib.last_error()
+
+
+def test_geom_create_rejects_bad_arguments():
+    import ctypes as C
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.scd_geom_create(None, C.byref(h)) == _lib.SCD_E_INVALID
+    desc = _lib.GeomDesc(n0=0, n1=8)
+    assert lib.scd_geom_create(C.byref(desc), C.byref(h)) == _lib.SCD_E_INVALID
+    assert 'invalid geometry' in _lib.last_error()
+    assert lib.scd_geom_destroy(None) == 0
+
+
+# ---------------------------------------------------------------- geometry ----
+def test_geometry_object():
+    g = pkg.ParallelBeamGeometry2D.from_im_shape((256, 256), 60)
+    o = O.OracleGeometry((256, 256), 60)
+    assert (g.n_det, g.x_min, g.s_min, g.ds) == (o.n_det, o.x_min, o.s_min, o.ds)
+    assert np.array_equal(g.angles, o.angles)
+    rt = pkg.B200RayTrafo((501, 501), 1200)
+    assert rt.obs_shape == (1200, 711) and rt.im_shape == (501, 501)
+    assert not hasattr(rt, 'resize')
+    assert isinstance(rt, pkg.BaseRayTrafo) and isinstance(rt, torch.nn.Module)
+    assert rt.to('cpu') is rt
+    with pytest.raises(NotImplementedError):
+        pkg.B200RayTrafo((64, 64), 10, impl='something')
+    assert pkg.SimpleTrafo is pkg.B200RayTrafo
+
+
+class _CpuTrafo(pkg.BaseRayTrafo):
+    """BaseRayTrafo subclass over the oracle matrices: exercises the adapters of the boundary type."""
+
+    def __init__(self, geom):
+        super().__init__(geom.im_shape, geom.obs_shape)
+        self.rt = O.OracleRayTrafo(geom)
+
+    def trafo(self, x):
+        return self.rt.trafo(x)
+
+    def trafo_adjoint(self, y):
+        return self.rt.trafo_adjoint(y)
+
+    trafo_flat = pkg.BaseRayTrafo._trafo_flat_via_trafo
+    trafo_adjoint_flat = pkg.BaseRayTrafo._trafo_adjoint_flat_via_trafo_adjoint
+
+
+def test_base_ray_trafo_adapters():
+    geom = O.OracleGeometry((16, 16), 5)
+    rt = _CpuTrafo(geom)
+    x = torch.rand(2, 3, 16, 16)
+    y = rt(x)
+    assert y.shape == (2, 3, 5, geom.n_det)
+    yf = rt.trafo_flat(x.reshape(6, -1).T)
+    assert yf.shape == (5 * geom.n_det, 6) and torch.equal(yf.T.reshape(y.shape), y)
+    xf = rt.trafo_adjoint_flat(yf)
+    assert torch.allclose(xf.T.reshape(x.shape), rt.trafo_adjoint(y))
+    with pytest.raises(NotImplementedError):
+        rt.fbp(y)
+
+
+# ------------------------------------------------------- schedule / DDPM -----
+def test_schedule_and_ddpm_match_reference_golden():
+    with open(os.path.join(GOLDEN, 'schedule.json')) as f:
+        ref = json.load(f)
+    for key, val in ref['jump'].items():
+        assert pkg._schedule_jump(*[int(v) for v in key.split(',')]) == val
+    sde = pkg.DDPM()
+    for n, pairs in ref['pairs'].items():
+        kw = {'num_steps': int(n), 'travel_length': 1, 'travel_repeat': 1}
+        s = pkg.BaseSampler(score=None, sde=sde, predictor=None, sample_kwargs=kw)
+        _, steps = s._schedule()
+        assert [list(p) for p in steps] == pairs
+    t = torch.tensor(ref['abar']['t'])
+    assert sde._compute_alpha_cumprod(t).numpy().view(np.uint32).tolist() == ref['abar']['bits']
+    assert sde.marginal_prob_mean(t).numpy().view(np.uint32).tolist() == ref['mean']
+    assert sde.marginal_prob_std(t).numpy().view(np.uint32).tolist() == ref['std']
+    assert np.array_equal(sde.alpha_bar_table().numpy(), np.load(os.path.join(GOLDEN, 'abar_table.npy')))
+    assert sde.prior_sampling([2, 1, 4, 4]).shape == (2, 1, 4, 4)
+    kw = {'num_steps': 100, 'travel_length': 1, 'travel_repeat': 1, 'early_stopping_pct': 0.5}
+    _, steps = pkg.BaseSampler(None, sde, None, kw)._schedule()
+    assert len(steps) == 50
+
+
+def test_ve_vp_schedules():
+    t = torch.tensor([0.1, 0.5, 1.0])
+    ve, vp = pkg.VESDE(0.01, 100), pkg.VPSDE(0.1, 10)
+    assert torch.allclose(ve.marginal_prob_std(t), 0.01 * (100 / 0.01) ** t)
+    assert torch.equal(ve.marginal_prob_mean(t), torch.ones(3))
+    lm = -0.25 * t ** 2 * 9.9 - 0.5 * t * 0.1
+    assert torch.allclose(vp.marginal_prob_mean(t), torch.exp(lm))
+    assert torch.allclose(vp.marginal_prob_std(t), torch.sqrt(1 - torch.exp(2 * lm)))
+    assert pkg._SCORE_PRED_CLASSES == [pkg.VPSDE, pkg.VESDE] and pkg._EPSILON_PRED_CLASSES == [pkg.DDPM]
+
+
+# ------------------------------------- generic (tensor-op) paths vs reference --
+def test_tweedie_and_ddim_tensor_paths_match_reference_golden(golden, monkeypatch):
+    """On CPU tensors apTweedy / ddim run as tensor ops (the path autograd uses): bit-exact vs reference."""
+    d = golden('tweedie_ddim.npz')
+    sde = pkg.DDPM()
+    x, s, xhat = (torch.from_numpy(d[k]) for k in ('x', 's', 'xhat'))
+    for ci, (t, tp) in enumerate(d['cases']):
+        tt, tpv = torch.ones(3) * float(t), torch.ones(3) * float(tp)
+        assert np.array_equal(pkg.apTweedy(s=s, x=x, sde=sde, time_step=tt).numpy(), d['tweedie_%d' % ci])
+        for eta in (0.0, 0.15, 0.85):
+            torch.manual_seed(77 + ci)
+            out = pkg.ddim(sde=sde, s=s, xhat=xhat, time_step=(tt, tpv), step_size=1, eta=eta,
+                           use_simplified_eqn=True)
+            assert np.array_equal(out.numpy(), d['ddim_%d_%g' % (ci, eta)])
+
+
+def test_cg_tensor_path_matches_reference_golden(golden):
+    d = golden('cg_small.npz')
+    rt = O.OracleRayTrafo(O.OracleGeometry((32, 32), 12))
+    x0, rhs = torch.from_numpy(d['x0']), torch.from_numpy(d['rhs'])
+    for gamma in (0.01, 1.0):
+        op = lambda v: v + gamma * rt.trafo_adjoint(rt(v))      # noqa: E731
+        for k in (0, 1, 2, 5):
+            out = pkg.cg(op=op, x=x0, rhs=rhs, n_iter=k).numpy()
+            # (p*d).sum vs norm()**2: same maths, different reduction -> round-off only
+            assert rel_l2(out, d['x_g%g_k%d' % (gamma, k)]) < (1e-6 if gamma < 1 else 5e-4)
+
+
+def test_sampler_with_generic_operator_matches_reference_chain(golden):
+    """BaseSampler + DDS predictor of this package, driven on CPU with the oracle operator,
+    reproduces the reference sampler's reconstruction (same seeds)."""
+    from scorenet import BlurScore
+    d = golden('dds_small.npz')
+    rt = O.OracleRayTrafo(O.OracleGeometry((64, 64), 16))
+    sde, score = pkg.DDPM(), BlurScore()
+    y = torch.from_numpy(d['y'])
+    kw = {'num_steps': 10, 'batch_size': 2, 'start_time_step': 0, 'im_shape': [1, 64, 64], 'eps': 1e-3,
+          'travel_length': 1, 'travel_repeat': 1,
+          'predictor': {'eta': 0.15, 'gamma': 0.05, 'use_simplified_eqn': True, 'ray_trafo': rt}}
+    predictor = functools.partial(pkg.decomposed_diffusion_sampling_sde_predictor, score=score, sde=sde,
+                                  rhs=rt.trafo_adjoint(y), cg_kwargs={'max_iter': 3})
+    sampler = pkg.BaseSampler(score=score, sde=sde, predictor=predictor, sample_kwargs=kw, device='cpu')
+    torch.manual_seed(11)
+    recon = sampler.sample(logging=False)
+    assert rel_l2(recon.numpy(), d['recon']) < 1e-5
+
+
+def test_adapted_predictor_and_adapt_run_with_autograd():
+    """SCD step on CPU with a tiny trainable score: _adapt changes the trainable parameters through
+    Tweedie -> CG -> loss, and the adapted predictor returns finite tensors of the right shape."""
+    geom = O.OracleGeometry((16, 16), 6)
+    rt = O.OracleRayTrafo(geom)
+
+    class LoraInjectedConv2d(torch.nn.Module):          # class name is what _has_lora() looks for
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(1, 1, 3, padding=1)
+            self.scale = 1.0
+
+        def forward(self, x):
+            return self.conv(x) * self.scale
+
+    class Score(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l = LoraInjectedConv2d()
+
+        def forward(self, x, t):
+            return 0.1 * x + self.l(x)
+
+    torch.manual_seed(0)
+    score, sde = Score(), pkg.DDPM()
+    gt = torch.rand(1, 1, 16, 16)
+    y = rt(gt)
+    rhs = rt.trafo_adjoint(y)
+    loss_fn = lambda x: torch.mean((rt(x) - y).pow(2)) + 1e-6 * pkg.tv_loss(x)   # noqa: E731
+    before = score.l.conv.weight.detach().clone()
+    x = torch.randn(1, 1, 16, 16)
+    t = torch.ones(1) * 500.
+    pkg._adapt(x=x, score=score, sde=sde, ray_trafo=rt, loss_fn=loss_fn, time_step=t, rhs=rhs, num_steps=2,
+               lr=1e-2, gamma=0.1, n_iter=1)
+    assert not torch.equal(before, score.l.conv.weight.detach())
+    adapt_fn = functools.partial(pkg._adapt, score=score, sde=sde, loss_fn=loss_fn, num_steps=1, lr=1e-3)
+    for dc in ('cg', 'gd', 'none'):
+        xn, x0 = pkg.adapted_ddim_sde_predictor(
+            score=score, sde=sde, x=x, time_step=(t, torch.ones(1) * 490.), eta=0.85, step_size=1,
+            adapt_fn=adapt_fn, use_adapt=True, ray_trafo=rt, add_cg=True, dc_type=dc, gamma=0.1,
+            cg_kwargs={'max_iter': 1}, rhs=rhs)
+        assert xn.shape == x.shape and torch.isfinite(xn).all() and torch.isfinite(x0).all()
+    assert score.l.scale == 1.0
+    assert float(pkg.tv_loss(torch.ones(1, 1, 4, 4))) == 0.0
+
+
+def test_factories_keep_reference_signatures():
+    import inspect
+    from diffusion_models_dev_project_b200.utils import exp_utils as E
+    assert list(inspect.signature(E.get_standard_sampler).parameters)[:8] == [
+        'args', 'config', 'score', 'sde', 'ray_trafo', 'observation', 'filtbackproj', 'device']
+    assert list(inspect.signature(E.get_standard_adapted_sampler).parameters)[:8] == [
+        'args', 'config', 'score', 'sde', 'ray_trafo', 'observation', 'device', 'complex_y']
+    assert list(inspect.signature(pkg.cg).parameters) == ['op', 'x', 'rhs', 'n_iter', 'tol']
+    assert list(inspect.signature(pkg.ddim).parameters) == [
+        'sde', 's', 'xhat', 'time_step', 'step_size', 'eta', 'use_simplified_eqn']
+    assert list(inspect.signature(pkg.decomposed_diffusion_sampling_sde_predictor).parameters) == [
+        'score', 'sde', 'x', 'rhs', 'time_step', 'eta', 'gamma', 'step_size', 'cg_kwargs', 'datafitscale',
+        'use_simplified_eqn', 'ray_trafo']
+    assert list(inspect.signature(pkg.adapted_ddim_sde_predictor).parameters) == [
+        'score', 'sde', 'x', 'time_step', 'eta', 'step_size', 'adapt_fn', 'use_adapt', 'datafitscale',
+        'use_simplified_eqn', 'ray_trafo', 'add_cg', 'dc_type', 'gamma', 'cg_kwargs', 'rhs']
+
+    class NS(dict):
+        __getattr__ = dict.__getitem__
+    cfg = NS(sde=NS(type='ddpm', beta_min=1e-4, beta_max=0.02, num_steps=1000),
+             data=NS(im_size=64), forward_op=NS(trafo_name='simple_trafo', num_angles=12, impl='odl'))
+    assert isinstance(E.get_standard_sde(cfg), pkg.DDPM)
+    rt = E.get_standard_ray_trafo(cfg)
+    assert isinstance(rt, pkg.B200RayTrafo) and rt.obs_shape[0] == 12
+
+
+def test_psnr():
+    gt = np.zeros((4, 4)); gt[0, 0] = 1.0
+    assert pkg.PSNR(gt, gt) == float('inf')
+    assert abs(pkg.PSNR(gt + 0.1, gt) - 20.0) < 1e-9

@@ -1,0 +1,94 @@
+"""World-size-2 tests of the multi-GPU partitioning logic on CPU (gloo backend)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, rel_l2
+from oracle import oracle as O
+from diffusion_models_dev_project_b200.sharding import AngleShardedRayTrafo, shard_range
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 8, 60, 1200, 501):
+        for world in (1, 2, 3, 4, 8):
+            parts = [shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class OracleBase:
+    """CPU stand-in with the `_fp/_bp(angle_range=)` surface of B200RayTrafo, backed by the oracle."""
+
+    def __init__(self, geom):
+        self.geom = geom
+        self.im_shape, self.obs_shape = geom.im_shape, geom.obs_shape
+        self.adj_scale = geom.adj_scale
+        self.angles = geom.angles
+
+    def _fp(self, x, angle_range=None):
+        y = torch.from_numpy(O.fp(self.geom, x.numpy()))
+        if angle_range is not None:
+            lo, hi = angle_range
+            mask = torch.zeros(self.obs_shape[0], 1)
+            mask[lo:hi] = 1
+            y = y * mask
+        return y
+
+    def _bp(self, y, scale, angle_range=None):
+        out = O.bp(self.geom, y.numpy(), angle_range=angle_range)
+        return torch.from_numpy(out) * (scale / self.geom.adj_scale)
+
+
+def _worker(rank, world, port, tmp):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import diffusion_models_dev_project_b200 as pkg
+        geom = O.OracleGeometry((24, 24), 10)
+        base = OracleBase(geom)
+        sh = AngleShardedRayTrafo(base, chunk=2)
+        assert sh.angle_range == shard_range(10, rank, world)
+        g = torch.Generator().manual_seed(0)            # same data on every rank (replicated vectors)
+        x = torch.rand(5, 1, 24, 24, generator=g)
+        y = torch.randn(5, 1, *geom.obs_shape, generator=g)
+        # A stays sharded: own rows only; gathered = full operator
+        yl = sh(x)
+        lo, hi = sh.angle_range
+        full = base._fp(x)
+        assert torch.equal(yl[..., lo:hi, :], full[..., lo:hi, :])
+        assert float(yl[..., :lo, :].abs().sum() + yl[..., hi:, :].abs().sum()) == 0.0
+        assert rel_l2(sh.gather_sinogram(yl).numpy(), full.numpy()) < 1e-6
+        # A*: partial images summed by all-reduce == single-process result
+        assert rel_l2(sh.trafo_adjoint(y).numpy(), base._bp(y, geom.adj_scale).numpy()) < 1e-6
+        # normal operator and CG on replicated vectors: identical on all ranks, equal to 1 process
+        gamma = 0.05
+        ref_op = lambda v: v + gamma * base._bp(base._fp(v), geom.adj_scale)      # noqa: E731
+        assert rel_l2(sh.normal_apply(x, gamma).numpy(), ref_op(x).numpy()) < 1e-6
+        sol = pkg.cg(op=sh.normal_op(gamma), x=x, rhs=x + 1.0, n_iter=3)
+        ref = pkg.cg(op=ref_op, x=x, rhs=x + 1.0, n_iter=3)
+        assert rel_l2(sol.numpy(), ref.numpy()) < 1e-5
+        gathered = [torch.empty_like(sol) for _ in range(world)]
+        dist.all_gather(gathered, sol)
+        assert all(torch.equal(gathered[0], t) for t in gathered)
+        # sample sharding: disjoint contiguous shards, no collective on the data path
+        blo, bhi = shard_range(5, rank, world)
+        mine = ref_op(x[blo:bhi])
+        assert torch.equal(mine, ref_op(x)[blo:bhi])
+        open(os.path.join(tmp, 'ok%d' % rank), 'w').write('ok')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_angle_and_sample_sharding_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert sorted(os.listdir(tmp_path)) == ['ok0', 'ok1']
