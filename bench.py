@@ -120,6 +120,17 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def measured_traffic():
+    """DRAM bytes per launch of our kernels at the bench batch, from the latest ncu capture
+    committed under profiles/ (rNN_traffic.json); None when no capture is available."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')))
+    if not files:
+        return None, None
+    with open(files[-1]) as f:
+        return json.load(f), os.path.basename(files[-1])
+
+
 def time_pairs():
     from diffusion_models_dev_project_b200 import _schedule_jump
     ts = _schedule_jump(REVERSE_STEPS, 1, 1)
@@ -389,8 +400,16 @@ def run_b200(args):
         sweep_small = kernel_sweep(rt, B, dev, hbm_peak)
         sweep_big = kernel_sweep(rt, args.kernel_batch, dev, hbm_peak) if args.kernel_batch else {}
         dom = max(('fp_joseph', 'bp_pixel_axpy_dot'), key=lambda k: sweep_small[k]['ms'])
-        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': sweep_small[dom]['GB/s'], 'peak': hbm_peak,
-                    'unit': 'GB/s', 'frac': sweep_small[dom]['frac_hbm'], 'traffic': None,
+        traffic, traffic_src = measured_traffic()
+        tr = None
+        if traffic is not None and B == 8:
+            names = ['fp_pack_kernel', 'fp_joseph_kernel'] if dom == 'fp_joseph' else ['bp_pixel_kernel']
+            if all(n in traffic for n in names):
+                tr = sum(traffic[n]['dram_bytes_per_launch'] for n in names)
+        roofline = {'bound': 'hbm', 'kernel': dom + (' (fp_pack + fp_joseph launches)' if dom == 'fp_joseph' else ''),
+                    'achieved': sweep_small[dom]['GB/s'], 'peak': hbm_peak,
+                    'unit': 'GB/s', 'frac': sweep_small[dom]['frac_hbm'], 'traffic': tr,
+                    'traffic_source': traffic_src,
                     'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs, burst copy)' if peak_kind == 'measured'
                     else 'fallback 6.65 TB/s',
                     'algorithmic_bytes_per_launch': BYTES[dom] * B, 'launch_ms': sweep_small[dom]['ms'],

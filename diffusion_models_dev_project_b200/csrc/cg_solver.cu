@@ -11,6 +11,7 @@
 // cg_update_p (the last p-update is skipped: its result is never read).
 #include "scd_internal.cuh"
 #include <algorithm>
+#include <cstring>
 
 struct CgLayout {
     size_t img, sino, part_stride;
@@ -48,7 +49,8 @@ extern "C" size_t scd_cg_workspace_bytes(const scd_geom_t *g, int batch)
 }
 
 int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs, float gamma,
-               int n_iter, int batch, void *work, size_t work_bytes, cudaStream_t st)
+               int n_iter, int batch, void *work, size_t work_bytes, cudaStream_t st,
+               const FpPrologue *first)
 {
     if (!g || !x || !x_in || !rhs || !work) { scd_set_error("scd_cg: null argument"); return SCD_E_INVALID; }
     if (batch <= 0) return 0;
@@ -72,17 +74,26 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     int rc;
 
     // r = rhs - x - gamma A*(A x);  p = r;  rr = ||r||^2
-    if ((rc = scd_launch_fp(g, x_in, q, batch, 0, g->n_angles, pack, L.pack_bytes, st))) return rc;
+    // (the Tweedie step that produces x_in and rhs may be fused into this projection's pack pass)
+    if ((rc = scd_launch_fp(g, x_in, q, batch, 0, g->n_angles, pack, L.pack_bytes, st, first))) return rc;
     BpEpilogue e0;
     e0.c_acc = -gs; e0.add1 = x_in; e0.c1 = -1.f; e0.add2 = rhs; e0.c2 = 1.f;
     e0.out2 = p; e0.dot_part = rr_a; e0.dot_stride = ps; e0.dot_with_add1 = 0;
     if ((rc = scd_launch_bp(g, q, r, batch, 0, g->n_angles, e0, st))) return rc;
     float *rr_old = rr_a, *rr_new = rr_b;
-    int rr_old_n = nbp;
+    int rr_old_n = nbp, rr_prev_n = nbp;
 
     for (int it = 0; it < n_iter; ++it) {
-        // d = p + gamma A*(A p);  pd = <p,d>
-        if ((rc = scd_launch_fp(g, p, q, batch, 0, g->n_angles, pack, L.pack_bytes, st))) return rc;
+        // p = r + beta p (fused into the pack pass, it >= 1);  d = p + gamma A*(A p);  pd = <p,d>
+        FpPrologue up;
+        memset(&up, 0, sizeof(up));
+        if (it > 0) {
+            up.mode = 1; up.p = p; up.r = r;
+            up.rr_new_part = rr_old; up.rr_new_n = rr_old_n;        // after the swap below: newest ||r||^2
+            up.rr_old_part = rr_new; up.rr_old_n = rr_prev_n;       // and the one before it
+            up.part_stride = ps;
+        }
+        if ((rc = scd_launch_fp(g, p, q, batch, 0, g->n_angles, pack, L.pack_bytes, st, it > 0 ? &up : nullptr))) return rc;
         BpEpilogue e1;
         e1.c_acc = gs; e1.add1 = p; e1.c1 = 1.f; e1.add2 = nullptr; e1.c2 = 0.f;
         e1.out2 = nullptr; e1.dot_part = pd; e1.dot_stride = ps; e1.dot_with_add1 = 1;
@@ -90,10 +101,7 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
         // the first update reads the start iterate and writes the result buffer
         if ((rc = scd_launch_cg_update_xr(it == 0 ? x_in : x, x, r, p, d, rr_old, rr_old_n, pd, nbp, ps, rr_new,
                                           batch, (int64_t)L.img, st))) return rc;
-        if (it + 1 < n_iter) {
-            if ((rc = scd_launch_cg_update_p(p, r, rr_new, nvec, rr_old, rr_old_n, ps, batch,
-                                             (int64_t)L.img, st))) return rc;
-        }
+        rr_prev_n = rr_old_n;
         std::swap(rr_old, rr_new);
         rr_old_n = nvec;
     }
@@ -105,7 +113,7 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
 extern "C" int scd_cg(const scd_geom_t *g, float *x, const float *rhs, double gamma, int n_iter,
                       int batch, void *work, size_t work_bytes, void *stream)
 {
-    return scd_cg_run(g, x, x, rhs, (float)gamma, n_iter, batch, work, work_bytes, (cudaStream_t)stream);
+    return scd_cg_run(g, x, x, rhs, (float)gamma, n_iter, batch, work, work_bytes, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" size_t scd_fp_scratch_bytes(const scd_geom_t *g, int batch)
@@ -174,11 +182,13 @@ extern "C" int scd_dds_step(const scd_geom_t *g, const float *x, const float *s,
     float *b = (float *)(w + L.off_b), *xh = (float *)(w + L.off_xh);
     const int64_t numel = (int64_t)L.img;
     int rc;
-    // xhat0 = Tweedie(x, s);  b = xhat0 + gamma*A*y
-    if ((rc = scd_launch_tweedie_rhs(x, s, atb, t, abar, n_table, (float)gamma, xhat0, b, batch, numel, st)))
-        return rc;
-    // CG starts from xhat0 but must not overwrite it (the predictor returns it)
-    if ((rc = scd_cg_run(g, xhat0, xh, b, (float)gamma, n_iter, batch, work, work_bytes, st))) return rc;
+    // xhat0 = Tweedie(x, s) and b = xhat0 + gamma*A*y are produced inside the pack pass of the
+    // first projection; CG starts from xhat0 but must not overwrite it (the predictor returns it)
+    FpPrologue tw;
+    memset(&tw, 0, sizeof(tw));
+    tw.mode = 2; tw.x = x; tw.s = s; tw.atb = atb; tw.t = t; tw.abar = abar; tw.n_table = n_table;
+    tw.gamma = (float)gamma; tw.xhat0 = xhat0; tw.b = b;
+    if ((rc = scd_cg_run(g, xhat0, xh, b, (float)gamma, n_iter, batch, work, work_bytes, st, &tw))) return rc;
     return scd_launch_ddim(xh, s, eps, t, t_prev, abar, n_table, (float)eta, (float)(eta * eta), x_next,
                            batch, numel, st);
 }

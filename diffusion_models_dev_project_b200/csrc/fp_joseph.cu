@@ -22,6 +22,7 @@
 #include "scd_internal.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 struct FpRun { int cls, first, count, cta0; };
 
@@ -61,59 +62,113 @@ struct FpParams {
 struct __align__(16) FpAngSmem { double a, b, c; float scale; int id; };
 
 // ------------------------------------------------------------------ pack ---
-// grid = (col tiles of 32, row tiles of 32 [over the padded row count], groups*2 classes)
-template <int S>
+// One block = one 32x32 image tile of one sample group; it writes the tile into BOTH packed
+// orientations (class 0 directly, class 1 through a shared-memory transpose), including the
+// zero pad pixels and the zero rows that round the row count up to a multiple of TR.
+// Optional prologue (the producer of the image is fused into the pack pass):
+//   mode 1  CG direction update   p = r + beta p        (reference src/utils/cg.py:35-38)
+//   mode 2  Tweedie + CG rhs      xhat0, b              (reference src/samplers/utils.py:370-378, :197)
+// grid = (tiles over axis 1, tiles over axis 0, groups), both tile ranges cover the padded rows.
+template <int S, int MODE>
 __global__ void __launch_bounds__(256)
-fp_pack_kernel(const FpParams P)
+fp_pack_kernel(const FpParams P, const FpPrologue Q)
 {
     __shared__ float tr[S][32][33];
-    const int cls = blockIdx.z & 1, grp = blockIdx.z >> 1;
-    const int nrows = cls == 0 ? P.n0 : P.n1, ncols = cls == 0 ? P.n1 : P.n0;
-    const int pitch = P.L.pitch[cls], prow = P.L.rows[cls];
+    __shared__ float coef[S][3];
+    const int grp = blockIdx.z;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8
-    const int R0 = blockIdx.y * 32, C0 = blockIdx.x * 32;
-    if (R0 >= prow || C0 >= ncols) return;
-    float *dst = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[cls];
+    const int K0 = blockIdx.y * 32, K1 = blockIdx.x * 32;
     const size_t isz = (size_t)P.n0 * P.n1;
+    float *dst0 = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[0];
+    float *dst1 = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[1];
+    const int pitch0 = P.L.pitch[0], pitch1 = P.L.pitch[1];
 
-    if (cls == 1) {
-        // transposed orientation: load [k0 = C0.., k1 = R0..] coalesced along k1, swap via smem
+    if (MODE != 0) {
+        // per-sample scalars, computed by one warp per sample
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (w < S) {
+            const int b = grp * S + w;
+            if (b < P.batch) {
+                if (MODE == 1) {
+                    float rn = 0.f, ro = 0.f;
+                    for (int i = lane; i < Q.rr_new_n; i += 32) rn += Q.rr_new_part[(size_t)b * Q.part_stride + i];
+                    for (int i = lane; i < Q.rr_old_n; i += 32) ro += Q.rr_old_part[(size_t)b * Q.part_stride + i];
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const int b = grp * S + s;
-            for (int i = ty; i < 32; i += 8) {
-                const int k0 = C0 + i, k1 = R0 + tx;
-                tr[s][i][tx] = (b < P.batch && k0 < P.n0 && k1 < P.n1) ? __ldg(P.img + b * isz + (size_t)k0 * P.n1 + k1) : 0.f;
+                    for (int off = 16; off > 0; off >>= 1) {
+                        rn += __shfl_xor_sync(0xffffffffu, rn, off);
+                        ro += __shfl_xor_sync(0xffffffffu, ro, off);
+                    }
+                    if (lane == 0) coef[w][0] = __fdiv_rn(rn, ro);           // beta
+                } else if (lane == 0) {
+                    long long idx = (long long)Q.t[b] + 1;                   // Tensor.long() + 1
+                    idx = idx < 0 ? 0 : (idx >= Q.n_table ? Q.n_table - 1 : idx);
+                    const float ab = Q.abar[idx];
+                    const float mean = __fsqrt_rn(ab);
+                    coef[w][0] = __fsqrt_rn(__fsub_rn(1.0f, ab));            // std_t
+                    coef[w][1] = __fdiv_rn(1.0f, mean);                      // mean_t^-1
+                }
             }
         }
         __syncthreads();
     }
+
+    // ---- produce the tile (prologue), plain outputs, class-0 packed rows ----
     for (int i = ty; i < 32; i += 8) {
-        const int r = R0 + i, c = C0 + tx;
-        if (r >= prow) break;
+        const int k0 = K0 + i, k1 = K1 + tx;
+        const bool in_img = k0 < P.n0 && k1 < P.n1;
         float v[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const int b = grp * S + s;
-            if (cls == 0)
-                v[s] = (b < P.batch && r < nrows && c < ncols) ? __ldg(P.img + b * isz + (size_t)r * P.n1 + c) : 0.f;
-            else
-                v[s] = tr[s][tx][i];           // (k0 = C0 + tx = c, k1 = R0 + i = r)
+            v[s] = 0.f;
+            if (in_img && b < P.batch) {
+                const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
+                if (MODE == 0) {
+                    v[s] = __ldg(P.img + o);
+                } else if (MODE == 1) {
+                    v[s] = fmaf(coef[s][0], Q.p[o], Q.r[o]);
+                    Q.p[o] = v[s];
+                } else {
+                    const float u = __fsub_rn(Q.x[o], __fmul_rn(Q.s[o], coef[s][0]));
+                    v[s] = __fmul_rn(u, coef[s][1]);
+                    Q.xhat0[o] = v[s];
+                    Q.b[o] = __fadd_rn(v[s], __fmul_rn(Q.gamma, Q.atb[o]));
+                }
+            }
+            tr[s][i][tx] = v[s];
         }
-        float *q = dst + ((size_t)r * pitch + 1 + c) * S;
-        if (c < ncols) {
+        if (k0 < P.L.rows[0] && k1 < P.n1) {
+            float *q = dst0 + ((size_t)k0 * pitch0 + 1 + k1) * S;
             if (S == 4) *reinterpret_cast<float4 *>(q) = make_float4(v[0], v[1], v[2], v[3]);
             else if (S == 2) *reinterpret_cast<float2 *>(q) = make_float2(v[0], v[1]);
             else q[0] = v[0];
-        }
-        // zero pads: left pad by the first column tile, right pads by the tile holding the last column
-        if (c == 0) {
+            if (k1 == 0) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) q[s - S] = 0.f;
-        }
-        if (c == ncols - 1) {
+                for (int s = 0; s < S; ++s) q[s - S] = 0.f;
+            }
+            if (k1 == P.n1 - 1) {
 #pragma unroll
-            for (int s = 0; s < 2 * S; ++s) q[S + s] = 0.f;
+                for (int s = 0; s < 2 * S; ++s) q[S + s] = 0.f;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- class-1 packed rows: row = k1, col = k0 (coalesced along k0) -------
+    for (int i = ty; i < 32; i += 8) {
+        const int k1 = K1 + i, k0 = K0 + tx;
+        if (k1 < P.L.rows[1] && k0 < P.n0) {
+            float *q = dst1 + ((size_t)k1 * pitch1 + 1 + k0) * S;
+            if (S == 4) *reinterpret_cast<float4 *>(q) = make_float4(tr[0][tx][i], tr[1 % S][tx][i], tr[2 % S][tx][i], tr[3 % S][tx][i]);
+            else if (S == 2) *reinterpret_cast<float2 *>(q) = make_float2(tr[0][tx][i], tr[1 % S][tx][i]);
+            else q[0] = tr[0][tx][i];
+            if (k0 == 0) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) q[s - S] = 0.f;
+            }
+            if (k0 == P.n0 - 1) {
+#pragma unroll
+                for (int s = 0; s < 2 * S; ++s) q[S + s] = 0.f;
+            }
         }
     }
 }
@@ -401,10 +456,23 @@ static int fp_launch_t(const FpParams &P, dim3 grid, int threads, size_t smem, c
     return 0;
 }
 
-int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
-                  int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st)
+template <int S>
+static int fp_pack_launch(const FpParams &P, const FpPrologue &Q, dim3 pg, cudaStream_t st)
 {
-    if (!g || !img || !sino) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
+    if (Q.mode == 0) fp_pack_kernel<S, 0><<<pg, 256, 0, st>>>(P, Q);
+    else if (Q.mode == 1) fp_pack_kernel<S, 1><<<pg, 256, 0, st>>>(P, Q);
+    else fp_pack_kernel<S, 2><<<pg, 256, 0, st>>>(P, Q);
+    SCD_LAUNCH_CHECK("fp_pack_kernel");
+    return 0;
+}
+
+int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
+                  int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                  const FpPrologue *prologue)
+{
+    FpPrologue Q;
+    if (prologue) Q = *prologue; else { memset(&Q, 0, sizeof(Q)); }
+    if (!g || (!img && Q.mode == 0) || !sino) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
         scd_set_error("scd_fp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",
                       batch, angle_lo, angle_hi, g->n_angles);
@@ -427,14 +495,15 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
     const unsigned gy = (unsigned)c.groups;
     if (gy > 32767u) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
 
-    // ---- pack: image -> tile-ready layout (both orientations) ----
+    // ---- pack: image -> tile-ready layout (both orientations), producer fused in ----
     {
-        const int maxr = std::max(c.L.rows[0], c.L.rows[1]), maxc = std::max(g->n0, g->n1);
-        dim3 pg((maxc + 31) / 32, (maxr + 31) / 32, gy * 2);
-        if (c.S == 1) fp_pack_kernel<1><<<pg, 256, 0, st>>>(P);
-        else if (c.S == 2) fp_pack_kernel<2><<<pg, 256, 0, st>>>(P);
-        else fp_pack_kernel<4><<<pg, 256, 0, st>>>(P);
-        SCD_LAUNCH_CHECK("fp_pack_kernel");
+        const int t0 = (std::max(g->n0, c.L.rows[0]) + 31) / 32, t1 = (std::max(g->n1, c.L.rows[1]) + 31) / 32;
+        dim3 pg(t1, t0, gy);
+        int rc;
+        if (c.S == 1) rc = fp_pack_launch<1>(P, Q, pg, st);
+        else if (c.S == 2) rc = fp_pack_launch<2>(P, Q, pg, st);
+        else rc = fp_pack_launch<4>(P, Q, pg, st);
+        if (rc) return rc;
     }
 
     // runs of order[] positions whose angle lies in [angle_lo, angle_hi), per class; a

@@ -64,9 +64,19 @@ struct scd_geom {
 // ------------------------------------------------------------ launchers ----
 // scratch: caller-owned device buffer of >= scd_fp_scratch_need(g, batch) bytes that
 // receives the packed ("tile-ready") copy of the image
+// Optional producer fused into the pack pass of the projector (img may be NULL then):
+//   mode 1: p = r + beta*p with beta = sum(rr_new_part)/sum(rr_old_part); writes p; projects p
+//   mode 2: xhat0 = (x - s*std_t)/mean_t, b = xhat0 + gamma*atb; writes both; projects xhat0
+struct FpPrologue {
+    int mode;
+    float *p; const float *r;
+    const float *rr_new_part; int rr_new_n; const float *rr_old_part; int rr_old_n; int part_stride;
+    const float *x, *s, *atb, *t, *abar; int n_table; float gamma;
+    float *xhat0, *b;
+};
 int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
                   int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, const FpPrologue *prologue = nullptr);
 size_t scd_fp_scratch_need(const scd_geom *g, int batch);
 
 // Backprojection with fused epilogue:
@@ -112,4 +122,4 @@ int scd_launch_ddim(const float *xhat, const float *s, const float *eps,
 // x_in: start iterate (read only), x_out: result (may alias x_in)
 int scd_cg_run(const scd_geom *g, const float *x_in, float *x_out, const float *rhs,
                float gamma, int n_iter, int batch, void *work, size_t work_bytes,
-               cudaStream_t st);
+               cudaStream_t st, const FpPrologue *first = nullptr);
