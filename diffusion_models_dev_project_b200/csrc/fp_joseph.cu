@@ -429,7 +429,7 @@ static FpConfig fp_choose(const scd_geom *g, int batch, int n_sel_angles)
     return c;
 }
 
-size_t scd_fp_scratch_need(const scd_geom *g, int batch)
+size_t scd_fp_scratch_need_v3(const scd_geom *g, int batch)
 {
     if (!g || batch <= 0) return 0;
     // the configuration may be overridden by tuning: size for the worst case (S = 1 packs least densely)
@@ -466,9 +466,9 @@ static int fp_pack_launch(const FpParams &P, const FpPrologue &Q, dim3 pg, cudaS
     return 0;
 }
 
-int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
+int scd_launch_fp_v3(const scd_geom *g, const float *img, float *sino, int batch,
                   int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
-                  const FpPrologue *prologue)
+                     const FpPrologue *prologue)
 {
     FpPrologue Q;
     if (prologue) Q = *prologue; else { memset(&Q, 0, sizeof(Q)); }

@@ -1,0 +1,775 @@
+// K1 (v4)  fp_march -- ray-driven Joseph forward projector A, batched over samples.
+//
+// Replaces SimpleTrafo.trafo (reference src/physics/trafo.py:58), which reaches ASTRA's par_fp
+// through ODL one image at a time.  Arithmetic follows SURVEY.md Appendix A: march along the
+// dominant axis, linear interpolation across it, weight dx/max(|cos|,|sin|), zero outside.
+//
+// The binding resource of Joseph's method is the shared-memory pipe (8 B per ray-step and
+// sample), so the layout is chosen to spend no wavefront on bank conflicts and none
+// on rays that miss the image:
+//
+//   packed image  packed[group][class][row][pixel][SB]   (fp_packq_kernel)
+//                 SB = V*LPR samples interleaved per pixel; class 1 is the transposed image so
+//                 the march is class-agnostic; 1 zero pixel left, 2 right, rows padded to x8.
+//   lanes         LPR consecutive lanes share one ray, each owns V samples (one LDS.(32V) per
+//                 tap).  With SB = 32 a quarter-warp reads exactly one pixel = one 128 B
+//                 wavefront whatever the ray spacing; SB = 16 conflicts only when neighbouring
+//                 rays are two pixels apart.
+//   warp          a "chunk" of RPW = 32/LPR adjacent rays; chunks of the NA angles of the CTA
+//                 are dealt round-robin to the 15 marching warps (NSLOT chunks per warp).  A
+//                 chunk whose rays all miss the image in a strip is skipped (warp vote).
+//   accumulators  registers, for the whole march: NSLOT*V per thread.
+//   strips        TR rows of the packed image = one contiguous byte range, fetched by a
+//                 producer warp with cp.async.bulk (TMA unit) into an mbarrier ring
+//                 (full/empty barriers; no CTA-wide barrier inside the march).
+//   cluster       for small batches the rows are split over a cluster of CS CTAs; partial line
+//                 integrals are exchanged through distributed shared memory and added in rank
+//                 order (deterministic, no atomics).
+#include "scd_internal.cuh"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+namespace cg = cooperative_groups;
+
+#define MQ_MAX_NBUF  8
+#define MQ_MAX_RUNS  8
+#define MQ_MAGIC      12582912.0f       /* 1.5 * 2^23: float add rounds to integer */
+#define MQ_MAGIC_BITS 0x4B400000
+
+struct MqRun { int cls, first, count, na, unit0; };   // `count` angles from order[first], `na` per unit
+
+struct MqLayout {
+    int SB;
+    int pitch[2];            // pixels per packed row, per class (ncols + 3)
+    int rows[2];             // packed rows per class (multiple of 8)
+    size_t cls_off[2];       // float offset of class c inside a group
+    size_t group_floats;     // floats per sample group
+};
+
+struct MqParams {
+    const float   *img;
+    float         *sino;
+    float         *packed;
+    const FpAngle *fp;
+    const int     *order;
+    int n0, n1, n_angles, n_det, batch;
+    int NA;                  // largest number of angles per CTA (sizes the tables)
+    int nbuf;                // ring depth
+    int CS;                  // cluster size = row split
+    int rows_per_cta;        // multiple of 8
+    int ring_bytes;          // strip ring (aliased by the partial sums), tables follow
+    int need_cls[2];
+    MqLayout L;
+    int n_runs;
+    MqRun runs[MQ_MAX_RUNS];
+};
+
+// ------------------------------------------------------------------ pack ---
+// One block = one 16x16 image tile of one sample group; it writes the tile into both packed
+// orientations, including the pad pixels and the zero rows that round the row count up to x8.
+// Optional prologue (the producer of the image is fused into the pack pass):
+//   mode 1  CG direction update   p = r + beta p        (reference src/utils/cg.py:35-38)
+//   mode 2  Tweedie + CG rhs      xhat0, b              (reference src/samplers/utils.py:370-378, :197)
+#define PK_T 16
+template <int MODE>
+__global__ void __launch_bounds__(256)
+fp_packq_kernel(const MqParams P, const FpPrologue Q)
+{
+    __shared__ __align__(16) float tile[PK_T * (PK_T + 1) * 36];
+    __shared__ float coef[32][2];
+    const int SB = P.L.SB;
+    const int SBP = SB >= 4 ? SB + 4 : SB + 1;
+    const int grp = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int K0 = blockIdx.y * PK_T, K1 = blockIdx.x * PK_T;
+    const size_t isz = (size_t)P.n0 * P.n1;
+
+    if (MODE != 0) {
+        // per-sample scalars, one warp per sample (8 warps, SB <= 32 samples)
+        const int w = tid >> 5, lane = tid & 31;
+        for (int s = w; s < SB; s += 8) {
+            const int b = grp * SB + s;
+            if (b >= P.batch) continue;
+            if (MODE == 1) {
+                float rn = 0.f, ro = 0.f;
+                for (int i = lane; i < Q.rr_new_n; i += 32) rn += Q.rr_new_part[(size_t)b * Q.part_stride + i];
+                for (int i = lane; i < Q.rr_old_n; i += 32) ro += Q.rr_old_part[(size_t)b * Q.part_stride + i];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    rn += __shfl_xor_sync(0xffffffffu, rn, off);
+                    ro += __shfl_xor_sync(0xffffffffu, ro, off);
+                }
+                if (lane == 0) coef[s][0] = __fdiv_rn(rn, ro);               // beta
+            } else if (lane == 0) {
+                long long idx = (long long)Q.t[b] + 1;                       // Tensor.long() + 1
+                idx = idx < 0 ? 0 : (idx >= Q.n_table ? Q.n_table - 1 : idx);
+                const float ab = Q.abar[idx];
+                const float mean = __fsqrt_rn(ab);
+                coef[s][0] = __fsqrt_rn(__fsub_rn(1.0f, ab));                // std_t
+                coef[s][1] = __fdiv_rn(1.0f, mean);                          // mean_t^-1
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- produce the tile: thread = pixel, loop over the samples of the group ----
+    {
+        const int ty = tid >> 4, tx = tid & 15;
+        const int k0 = K0 + ty, k1 = K1 + tx;
+        const bool in_img = k0 < P.n0 && k1 < P.n1;
+        float *tp = tile + (ty * (PK_T + 1) + tx) * SBP;
+        for (int s = 0; s < SB; ++s) {
+            const int b = grp * SB + s;
+            float v = 0.f;
+            if (in_img && b < P.batch) {
+                const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
+                if (MODE == 0) {
+                    v = __ldg(P.img + o);
+                } else if (MODE == 1) {
+                    v = fmaf(coef[s][0], Q.p[o], Q.r[o]);
+                    Q.p[o] = v;
+                } else {
+                    const float u = __fsub_rn(Q.x[o], __fmul_rn(Q.s[o], coef[s][0]));
+                    v = __fmul_rn(u, coef[s][1]);
+                    Q.xhat0[o] = v;
+                    Q.b[o] = __fadd_rn(v, __fmul_rn(Q.gamma, Q.atb[o]));
+                }
+            }
+            tp[s] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- write both orientations: lanes = (pixel, quad of samples), 16 B (or 4*V B) per lane ----
+    const int VQ = SB >= 4 ? 4 : SB;              // floats per lane
+    const int LQ = SB / VQ;                       // lanes per pixel
+    float *dst = P.packed + (size_t)grp * P.L.group_floats;
+#pragma unroll 1
+    for (int cls = 0; cls < 2; ++cls) {
+        if (!P.need_cls[cls]) continue;
+        const int pitch = P.L.pitch[cls];
+        const int nrow_img = cls == 0 ? P.n0 : P.n1;     // rows with data
+        const int ncol = cls == 0 ? P.n1 : P.n0;
+        const int nrow_pk = P.L.rows[cls];
+        float *d = dst + P.L.cls_off[cls];
+        for (int idx = tid; idx < PK_T * PK_T * LQ; idx += 256) {
+            const int q = idx % LQ, pix = idx / LQ;
+            const int cl = pix % PK_T, rl = pix / PK_T;          // column fastest -> contiguous stores
+            const int row = (cls == 0 ? K0 : K1) + rl, col = (cls == 0 ? K1 : K0) + cl;
+            if (row >= nrow_pk || col >= ncol) continue;
+            const float *tp = tile + (cls == 0 ? (rl * (PK_T + 1) + cl) : (cl * (PK_T + 1) + rl)) * SBP + q * VQ;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (row < nrow_img) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < VQ) v[i] = tp[i];
+            }
+            float *o = d + ((size_t)row * pitch + 1 + col) * SB + q * VQ;
+            if (VQ == 4) *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            else if (VQ == 2) *reinterpret_cast<float2 *>(o) = make_float2(v[0], v[1]);
+            else o[0] = v[0];
+            if (col == 0) {
+                for (int i = 0; i < VQ; ++i) o[i - SB] = 0.f;
+            }
+            if (col == ncol - 1) {
+                for (int i = 0; i < VQ; ++i) { o[SB + i] = 0.f; o[2 * SB + i] = 0.f; }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------- march ---
+__device__ __forceinline__ unsigned mq_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mq_mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(mq_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mq_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(mq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mq_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(mq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mq_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MQ_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MQ_DONE;\n"
+        "bra MQ_WAIT;\n"
+        "MQ_DONE:\n"
+        "}\n" :: "r"(mq_smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit, completion on an mbarrier
+__device__ __forceinline__ void mq_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(mq_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mq_smem_u32(bar)) : "memory");
+}
+
+// Tap loads with explicit 32-bit shared-window addresses (a generic pointer would be re-mapped
+// through the cluster window on every access).  volatile: they stay behind the mbarrier wait.
+template <int V> struct MqVec;
+template <> struct MqVec<1> {
+    typedef float T;
+    template <int OFF> static __device__ __forceinline__ T ld(unsigned a)
+    { T v; asm volatile("ld.shared.f32 %0, [%1+%2];\n" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
+};
+template <> struct MqVec<2> {
+    typedef float2 T;
+    template <int OFF> static __device__ __forceinline__ T ld(unsigned a)
+    { T v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];\n" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF)); return v; }
+};
+template <> struct MqVec<4> {
+    typedef float4 T;
+    template <int OFF> static __device__ __forceinline__ T ld(unsigned a)
+    {
+        T v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+        return v;
+    }
+};
+
+// acc += l*wl + r*w for the V samples of a lane.  V >= 2 uses the packed fp32x2 FMA of sm_100
+// (FFMA2: two independent round-to-nearest FMAs per issue slot, same results as two FFMAs).
+__device__ __forceinline__ void mq_tap(float (&p)[1], float l, float r, float wl, float w)
+{ p[0] = fmaf(r, w, fmaf(l, wl, p[0])); }
+__device__ __forceinline__ void mq_tap(float (&p)[2], float2 l, float2 r, float wl, float w)
+{
+    float2 a = make_float2(p[0], p[1]);
+    a = __ffma2_rn(l, make_float2(wl, wl), a);
+    a = __ffma2_rn(r, make_float2(w, w), a);
+    p[0] = a.x; p[1] = a.y;
+}
+__device__ __forceinline__ void mq_tap(float (&p)[4], float4 l, float4 r, float wl, float w)
+{
+    const float2 wl2 = make_float2(wl, wl), w2 = make_float2(w, w);
+    float2 a = make_float2(p[0], p[1]), b = make_float2(p[2], p[3]);
+    a = __ffma2_rn(make_float2(l.x, l.y), wl2, a);
+    b = __ffma2_rn(make_float2(l.z, l.w), wl2, b);
+    a = __ffma2_rn(make_float2(r.x, r.y), w2, a);
+    b = __ffma2_rn(make_float2(r.z, r.w), w2, b);
+    p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+}
+
+struct __align__(8) MqAng { float scale; int id; };
+
+// V     samples per lane (vector width of a tap)
+// LPR   lanes per ray            -> SB = V*LPR samples per group, RPW = 32/LPR rays per warp
+// NSLOT ray chunks per warp      (accumulators: NSLOT*V registers)
+// TR    rows per strip
+// NWT   warps per CTA: NWT-1 marching warps + one producer warp
+template <int V, int LPR, int NSLOT, int TR, int NWT>
+__global__ void __launch_bounds__(32 * NWT, 1)
+fp_march_kernel(const MqParams P)
+{
+    typedef MqVec<V> LD;
+    typedef typename LD::T VT;
+    constexpr int SB = V * LPR;
+    constexpr int RPW = 32 / LPR;
+    constexpr int NW = NWT - 1;
+    constexpr int NTHR = 32 * NWT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int CS = P.CS;
+    const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
+    const int grp = (int)blockIdx.x / CS;
+    const int unit = (int)blockIdx.y;
+
+    // locate this unit's run without indexing the parameter array dynamically
+    MqRun R = P.runs[0];
+#pragma unroll
+    for (int k = 1; k < MQ_MAX_RUNS; ++k)
+        if (k < P.n_runs && unit >= P.runs[k].unit0) R = P.runs[k];
+    const int pos0 = R.first + (unit - R.unit0) * R.na;
+    const int na = min(R.na, R.first + R.count - pos0);
+    const int cls = R.cls;
+    const int nrows = cls == 0 ? P.n0 : P.n1;   // marching axis
+    const int ncols = cls == 0 ? P.n1 : P.n0;   // interpolation axis
+    const int pitch = P.L.pitch[cls];
+    const int n_det = P.n_det;
+    const int b0 = grp * SB;
+    const unsigned row_bytes = (unsigned)(pitch * SB * 4);
+    const unsigned strip_bytes = TR * row_bytes;
+
+    // this CTA's rows: [r_begin, r_begin + nst*TR), inside the zero-padded packed rows
+    const int r_begin = rank * P.rows_per_cta;
+    const int r_end = min(r_begin + P.rows_per_cta, (nrows + 7) & ~7);
+    const int nst = r_end > r_begin ? (r_end - r_begin) / TR : 0;
+
+    // shared memory: strips[nbuf] (aliased by the partial line integrals red[SB][E] once the
+    // march is over) | mbarriers | angle table | ray table (u0, b)
+    const int NBUF = P.nbuf;
+    unsigned char *tile0 = smem_raw;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + P.ring_bytes);
+    unsigned long long *empty = full + MQ_MAX_NBUF;
+    MqAng *ang = reinterpret_cast<MqAng *>(empty + MQ_MAX_NBUF);
+    float2 *rays = reinterpret_cast<float2 *>(ang + P.NA);
+    float *red = reinterpret_cast<float *>(smem_raw);
+
+    const int E = na * n_det;
+    const float *src = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[cls] +
+                       (size_t)r_begin * pitch * SB;
+
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) { mq_mbar_init(&full[i], 1); mq_mbar_init(&empty[i], NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int e = tid; e < E; e += NTHR) {
+        const int ai = e / n_det, j = e - ai * n_det;
+        const int id = P.order[pos0 + ai];
+        const FpAngle f = P.fp[id];
+        // zf = u + 1 (left pad pixel): floor(zf) = packed pixel of the left tap
+        rays[e] = make_float2((float)(f.a * (double)j + (f.c + 1.0)), (float)f.b);
+        if (j == 0) { MqAng a; a.scale = f.scale; a.id = id; ang[ai] = a; }
+    }
+    __syncthreads();                              // mbarrier init + tables visible
+
+    float acc[NSLOT][V];
+    int eidx[NSLOT];
+    unsigned livemask = 0;
+    const int nchunk = (n_det + RPW - 1) / RPW;
+    const int NCH = na * nchunk;
+    const int lr = lane / LPR, lq = lane - lr * LPR;
+#pragma unroll
+    for (int k = 0; k < NSLOT; ++k) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[k][v] = 0.f;
+        const int C = warp + k * NW;
+        eidx[k] = 0;
+        if (warp < NW && C < NCH) {
+            const int ai = C / nchunk, cc = C - ai * nchunk;
+            const int j = cc * RPW + lr;
+            if (j < n_det) livemask |= 1u << k;
+            eidx[k] = ai * n_det + min(j, n_det - 1);
+        }
+    }
+
+    if (warp == NW) {
+        // ------------------------------ producer warp ------------------------------
+        if (lane == 0) {
+            int bi = 0; unsigned ph = 0;
+            for (int st = 0; st < nst; ++st) {
+                if (st >= NBUF) mq_mbar_wait(&empty[bi], ph ^ 1u);      // previous use of this buffer released
+                mq_mbar_expect_tx(&full[bi], strip_bytes);
+                mq_bulk_g2s(tile0 + (size_t)bi * strip_bytes, src + (size_t)st * TR * pitch * SB, strip_bytes, &full[bi]);
+                if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------ marching warps -----------------------------
+        const float zmax = (float)(ncols + 1);    // u = ncols: both taps on the right pads
+        // shared-window address of this lane's samples in pixel 0 of row 0 of buffer 0, with the
+        // mantissa offset of the floor trick folded in
+        const unsigned lane_base = mq_smem_u32(tile0) + (unsigned)(lq * V * 4) - (unsigned)MQ_MAGIC_BITS * (unsigned)(SB * 4);
+        const unsigned rays_base = mq_smem_u32(rays);
+        int bi = 0; unsigned ph = 0;
+        for (int st = 0; st < nst; ++st) {
+            mq_mbar_wait(&full[bi], ph);
+            const unsigned sbuf = lane_base + (unsigned)bi * strip_bytes;
+            const float r0f = (float)(r_begin + st * TR);
+#pragma unroll
+            for (int k = 0; k < NSLOT; ++k) {
+                if (warp + k * NW < NCH) {                              // warp-uniform
+                    const float2 ub = MqVec<2>::ld<0>(rays_base + (unsigned)eidx[k] * 8u);
+                    const float bf = ub.y;
+                    const float z0 = fmaf(r0f, bf, ub.x);
+                    const float z1 = fmaf((float)(TR - 1), bf, z0);
+                    // every ray of this chunk outside the image on every row of the strip
+                    const bool outside = !((livemask >> k) & 1u) || fmaxf(z0, z1) <= 0.0f || fminf(z0, z1) >= zmax;
+                    if (!__all_sync(0xffffffffu, outside)) {
+                        float w[TR];
+                        unsigned ad[TR];
+#pragma unroll
+                        for (int rr = 0; rr < TR; ++rr) {
+                            // clamped position: outside the image both taps land on zero pad pixels
+                            const float z = fminf(fmaxf(fmaf((float)rr, bf, z0), 0.0f), zmax);
+                            const float t = __fadd_rd(z, MQ_MAGIC);       // floor(z) in the mantissa
+                            w[rr] = z - (t - MQ_MAGIC);
+                            ad[rr] = sbuf + rr * row_bytes + (unsigned)__float_as_int(t) * (unsigned)(SB * 4);
+                        }
+                        VT tl[TR], tr[TR];
+#pragma unroll
+                        for (int rr = 0; rr < TR; ++rr) {
+                            tl[rr] = LD::template ld<0>(ad[rr]);
+                            tr[rr] = LD::template ld<SB * 4>(ad[rr]);
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < TR; ++rr) mq_tap(acc[k], tl[rr], tr[rr], 1.0f - w[rr], w[rr]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mq_mbar_arrive(&empty[bi]);                   // this warp is done with buffer bi
+            if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+        }
+    }
+    __syncthreads();                              // all strips consumed: the ring can be reused
+
+    // ---- partial line integrals -> red[s][e] ------------------------------
+    if (warp < NW) {
+#pragma unroll
+        for (int k = 0; k < NSLOT; ++k) {
+            if ((livemask >> k) & 1u) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) red[(size_t)(lq * V + v) * E + eidx[k]] = acc[k][v];
+            }
+        }
+    }
+    if (CS > 1) cluster.sync(); else __syncthreads();
+
+    // ---- add the row-split partials in rank order, scale, write (coalesced along the detector) ----
+    const int per = (E + CS - 1) / CS;
+    const int e_lo = rank * per, e_hi = min(E, e_lo + per);
+    const int cnt = max(e_hi - e_lo, 0);
+    const size_t sino_sz = (size_t)P.n_angles * n_det;
+    for (int idx = tid; idx < cnt * SB; idx += NTHR) {
+        const int s = idx / cnt, e = e_lo + (idx - s * cnt);
+        float v;
+        if (CS > 1) {
+            v = 0.f;
+            for (int r = 0; r < CS; ++r) v += cluster.map_shared_rank(red, r)[(size_t)s * E + e];
+        } else {
+            v = red[(size_t)s * E + e];
+        }
+        if (b0 + s < P.batch) {
+            const int ai = e / n_det, j = e - ai * n_det;
+            P.sino[(size_t)(b0 + s) * sino_sz + (size_t)ang[ai].id * n_det + j] = v * ang[ai].scale;
+        }
+    }
+    if (CS > 1) cluster.sync();                   // keep red alive until every rank has read it
+}
+
+// ------------------------------------------------------------- host side ---
+struct MqConfig {
+    int V, LPR, SB, NSLOT, TR, NWT, NA, CS, nbuf, rows_per_cta, groups;
+    MqLayout L;
+    size_t smem, scratch_bytes, ring_bytes;
+};
+
+static MqLayout mq_layout(const scd_geom *g, int SB)
+{
+    MqLayout L;
+    L.SB = SB;
+    const int nr[2] = {g->n0, g->n1}, nc[2] = {g->n1, g->n0};
+    size_t off = 0;
+    for (int c = 0; c < 2; ++c) {
+        L.pitch[c] = nc[c] + 3;
+        L.rows[c] = (nr[c] + 7) & ~7;
+        L.cls_off[c] = off;
+        off += (size_t)L.rows[c] * L.pitch[c] * SB;
+        off = (off + 31) & ~(size_t)31;            // keep every class 128-byte aligned
+    }
+    L.group_floats = off;
+    return L;
+}
+
+static size_t mq_fixed_smem(const scd_geom *g, int NA)
+{
+    return 2 * MQ_MAX_NBUF * 8 + sizeof(MqAng) * NA + 8 * (size_t)NA * g->n_det + 64;
+}
+
+static bool mq_have_tr(int V, int LPR, int TR)
+{
+    if (LPR == 1) return TR == 8 || (V == 4 && TR == 4);
+    if (LPR == 2) return TR == 8 || TR == 4;
+    if (LPR == 4) return TR == 4 || TR == 2;
+    return TR == 2;                                // LPR == 8
+}
+
+// slot counts instantiated per CTA shape: 16 warps (15 marching, 128 registers) / 32 warps (31 marching, 64 registers)
+static int mq_nslot(int nwt, int need)
+{
+    if (nwt == 16) return need <= 6 ? 6 : (need <= 13 ? 13 : 0);
+    return need <= 3 ? 3 : (need <= 6 ? 6 : 0);
+}
+
+static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
+{
+    MqConfig c;
+    // samples per group: one lane carries up to 4 samples, up to 8 lanes share a ray
+    if (batch <= 1) { c.V = 1; c.LPR = 1; }
+    else if (batch == 2) { c.V = 2; c.LPR = 1; }
+    else if (batch <= 4) { c.V = 4; c.LPR = 1; }
+    else if (batch <= 8) { c.V = 4; c.LPR = 2; }
+    else { c.V = 4; c.LPR = 4; }
+    if (g->tune_fp_samples) {
+        const int sb = g->tune_fp_samples;
+        if (sb == 1) { c.V = 1; c.LPR = 1; } else if (sb == 2) { c.V = 2; c.LPR = 1; }
+        else if (sb == 4) { c.V = 4; c.LPR = 1; } else if (sb == 8) { c.V = 4; c.LPR = 2; }
+        else if (sb == 16) { c.V = 4; c.LPR = 4; } else if (sb == 32) { c.V = 4; c.LPR = 8; }
+    }
+    const int maxpitch = std::max(g->n0, g->n1) + 3;
+    const size_t budget = (size_t)g->smem_optin;
+    // two strips of the thinnest kind must fit next to the tables, else fewer samples per group
+    for (;;) {
+        c.SB = c.V * c.LPR;
+        const int trmin = c.LPR >= 4 ? 2 : (c.LPR == 2 || c.V == 4 ? 4 : 8);
+        if (2 * (size_t)trmin * maxpitch * c.SB * 4 + mq_fixed_smem(g, 1) <= budget) break;
+        if (c.LPR > 1) c.LPR >>= 1; else if (c.V > 1) c.V >>= 1; else break;
+    }
+    c.SB = c.V * c.LPR;
+    c.groups = (batch + c.SB - 1) / c.SB;
+    const int RPW = 32 / c.LPR;
+    const int nchunk = (g->n_det + RPW - 1) / RPW;
+
+    c.NWT = (g->tune_fp_threads == 1024 && c.V == 4) ? 32 : 16;
+    const int NW = c.NWT - 1;
+    // angles per CTA and cluster row split.  Sharing a strip between NA angles divides the
+    // L2 -> SM traffic by NA, but the machine wants >= ~3/4 * SMs CTAs: take the largest NA for
+    // which a row split of at most 4 provides them (measured: tools/kbench.py --kernel fp --sweep)
+    const int maxrows8 = (std::max(g->n0, g->n1) + 7) & ~7;
+    int na = 4, cs = 1;
+    for (na = 4; na >= 1; na >>= 1) {
+        if (na > 1 && !mq_nslot(c.NWT, (na * nchunk + NW - 1) / NW)) continue;
+        const int units = c.groups * ((n_cls_max + na - 1) / na) * 2;
+        bool ok = false;
+        for (cs = 1; cs <= 4; cs <<= 1)
+            if (units * cs * 4 >= g->sm_count * 3 || maxrows8 / (cs * 2) < 16) { ok = units * cs * 4 >= g->sm_count * 3; break; }
+        if (cs > 4) cs = 4;
+        if (ok || na == 1) break;
+    }
+    na = std::max(na, 1);
+    if (g->tune_fp_angles) { na = g->tune_fp_angles; }
+    na = std::max(1, std::min(na, std::max(1, n_cls_max)));
+    while (na > 1 && !mq_nslot(c.NWT, (na * nchunk + NW - 1) / NW)) --na;
+    c.NA = na;
+    c.NSLOT = mq_nslot(c.NWT, (c.NA * nchunk + NW - 1) / NW);
+
+    // rows per strip / ring depth from the shared-memory budget
+    const int trs[3] = {8, 4, 2};
+    c.TR = 0;
+    for (int i = 0; i < 3; ++i) {
+        const int tr = trs[i];
+        if (g->tune_fp_rows && tr != g->tune_fp_rows) continue;
+        if (!mq_have_tr(c.V, c.LPR, tr)) continue;
+        if (3 * (size_t)tr * maxpitch * c.SB * 4 + mq_fixed_smem(g, c.NA) <= budget || tr == 2 ||
+            (tr == 4 && !mq_have_tr(c.V, c.LPR, 2))) { c.TR = tr; break; }
+    }
+    if (!c.TR) c.TR = mq_have_tr(c.V, c.LPR, 2) ? 2 : (mq_have_tr(c.V, c.LPR, 4) ? 4 : 8);
+    c.L = mq_layout(g, c.SB);
+    const size_t strip = (size_t)c.TR * maxpitch * c.SB * 4;
+
+    const int maxrows = std::max(c.L.rows[0], c.L.rows[1]);
+    if (g->tune_fp_cluster) cs = g->tune_fp_cluster;
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 1;
+    c.CS = cs;
+    c.rows_per_cta = (((maxrows + cs - 1) / cs) + 7) & ~7;
+
+    int nstrips = (c.rows_per_cta + c.TR - 1) / c.TR;
+    int nbuf = g->tune_fp_nbuf ? g->tune_fp_nbuf : MQ_MAX_NBUF;
+    nbuf = std::max(2, std::min(std::min(nbuf, MQ_MAX_NBUF), nstrips));
+    while (nbuf > 1 && nbuf * strip + mq_fixed_smem(g, c.NA) > budget) --nbuf;
+    c.nbuf = nbuf;
+    // the partials red[SB][NA*n_det] alias the ring
+    c.ring_bytes = (std::max(nbuf * strip, (size_t)c.SB * c.NA * g->n_det * 4) + 127) & ~(size_t)127;
+    c.smem = c.ring_bytes + mq_fixed_smem(g, c.NA);
+    c.scratch_bytes = (size_t)c.groups * c.L.group_floats * 4;
+    return c;
+}
+
+// ---- unit plan: which angles share a CTA ------------------------------------------------------
+// All CTAs cost about (angles + const), and there are only a few hundred of them for ~148 SMs, so
+// equal chunks of NA angles can leave a third of the machine idle in the last round.  The plan
+// splits each class into chunks of NA angles followed by shorter ones (launched last, largest
+// first: list scheduling) and keeps the split with the smallest simulated makespan.
+struct MqPlan { int n_runs; MqRun runs[MQ_MAX_RUNS]; int units; };
+
+static double mq_makespan(const int *sizes, const int *counts, int nkinds, int jobs_per_unit, int machines)
+{
+    // machines take jobs in launch order; all jobs of one kind cost the same
+    std::vector<double> load((size_t)machines, 0.0);
+    std::make_heap(load.begin(), load.end(), std::greater<double>());
+    for (int k = 0; k < nkinds; ++k) {
+        const double cost = sizes[k] + 0.25;
+        for (long j = 0; j < (long)counts[k] * jobs_per_unit; ++j) {
+            std::pop_heap(load.begin(), load.end(), std::greater<double>());
+            load.back() += cost;
+            std::push_heap(load.begin(), load.end(), std::greater<double>());
+        }
+    }
+    return *std::max_element(load.begin(), load.end());
+}
+
+static MqPlan mq_plan(const scd_geom *g, const MqConfig &c, int angle_lo, int angle_hi)
+{
+    // positions in order[] of the selected angles, per class (contiguous: order[] is sorted by
+    // class then index and the selection is an index range)
+    int first[2] = {-1, -1}, cnt[2] = {0, 0};
+    for (int pos = 0; pos < g->n_angles; ++pos) {
+        const int a = g->h_order[pos];
+        if (a < angle_lo || a >= angle_hi) continue;
+        const int cls = g->h_fp[a].cls;
+        if (first[cls] < 0) first[cls] = pos;
+        cnt[cls]++;
+    }
+    const int machines = std::max(1, g->sm_count / c.CS);
+    const int NA = c.NA;
+    // candidate: per class, `t1` angles alone, `t2` angles in pairs, the rest in chunks of NA
+    // (plus one remainder chunk); the same (t1, t2) for both classes, clipped to the class size
+    int best_t1 = 0, best_t2 = 0;
+    double best = -1.0;
+    const int nmax = std::max(cnt[0], cnt[1]);
+    const bool search = NA > 2 && g->tune_fp_plan != 1 && (long)c.groups * nmax * 2 <= 4096;
+    for (int t1 = 0; t1 <= (search ? std::min(nmax, 2 * NA) : 0); ++t1)
+        for (int t2 = 0; t2 + t1 <= (search ? std::min(nmax, 6 * NA) : 0); t2 += 2) {
+            int sizes[8], counts[8], nk = 0;
+            // launch order: big chunks of both classes, remainders, pairs, singles
+            int rem[2], big[2], pairs[2], single[2];
+            for (int cl = 0; cl < 2; ++cl) {
+                single[cl] = std::min(t1, cnt[cl]);
+                pairs[cl] = std::min(t2, cnt[cl] - single[cl]) / 2;
+                const int rest = cnt[cl] - single[cl] - 2 * pairs[cl];
+                big[cl] = rest / NA; rem[cl] = rest % NA;
+            }
+            sizes[nk] = NA; counts[nk++] = big[0] + big[1];
+            for (int cl = 0; cl < 2; ++cl) if (rem[cl]) { sizes[nk] = rem[cl]; counts[nk++] = 1; }
+            sizes[nk] = 2; counts[nk++] = pairs[0] + pairs[1];
+            sizes[nk] = 1; counts[nk++] = single[0] + single[1];
+            const double m = mq_makespan(sizes, counts, nk, c.groups, machines);
+            if (best < 0 || m < best - 1e-9) { best = m; best_t1 = t1; best_t2 = t2; }
+        }
+    MqPlan pl;
+    pl.n_runs = 0; pl.units = 0;
+    int used[2] = {0, 0};
+    auto add = [&](int cl, int count, int na) {
+        if (count <= 0) return;
+        MqRun &r = pl.runs[pl.n_runs++];
+        r.cls = cl; r.first = first[cl] + used[cl]; r.count = count; r.na = na; r.unit0 = pl.units;
+        pl.units += (count + na - 1) / na;
+        used[cl] += count;
+    };
+    int single[2], pairs[2], rest[2];
+    for (int cl = 0; cl < 2; ++cl) {
+        single[cl] = std::min(best_t1, cnt[cl]);
+        pairs[cl] = std::min(best_t2, cnt[cl] - single[cl]) / 2;
+        rest[cl] = cnt[cl] - single[cl] - 2 * pairs[cl];
+    }
+    for (int cl = 0; cl < 2; ++cl) add(cl, rest[cl], NA);          // includes the remainder chunk (run-local min)
+    for (int cl = 0; cl < 2; ++cl) add(cl, 2 * pairs[cl], 2);
+    for (int cl = 0; cl < 2; ++cl) add(cl, single[cl], 1);
+    return pl;
+}
+
+size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch)
+{
+    if (!g || batch <= 0) return 0;
+    size_t need = 0;
+    for (int SB = 1; SB <= 32; SB <<= 1) {
+        const MqLayout L = mq_layout(g, SB);
+        need = std::max(need, (size_t)((batch + SB - 1) / SB) * L.group_floats * 4);
+    }
+    return need + 256;
+}
+
+template <int V, int LPR, int NSLOT, int TR, int NWT>
+static int mq_launch_t(const MqParams &P, dim3 grid, size_t smem, cudaStream_t st)
+{
+    static int configured_smem = -1;     // per instantiation
+    if ((int)smem > configured_smem) {
+        SCD_CUDA(cudaFuncSetAttribute(fp_march_kernel<V, LPR, NSLOT, TR, NWT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_smem = (int)smem;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(32 * NWT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = P.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SCD_CUDA(cudaLaunchKernelEx(&cfg, fp_march_kernel<V, LPR, NSLOT, TR, NWT>, P));
+    SCD_LAUNCH_CHECK("fp_march_kernel");
+    return 0;
+}
+
+int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, int batch,
+                     int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                     const FpPrologue *prologue)
+{
+    FpPrologue Q;
+    if (prologue) Q = *prologue; else { memset(&Q, 0, sizeof(Q)); }
+    // angles of each class inside the range
+    int ncls[2] = {0, 0};
+    for (int a = angle_lo; a < angle_hi; ++a) ncls[g->h_fp[a].cls]++;
+    MqConfig c = mq_choose(g, batch, std::max(ncls[0], ncls[1]));
+    if (c.smem > (size_t)g->smem_optin || !c.NSLOT) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
+    const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
+    if (!scratch || sp + c.scratch_bytes > (uintptr_t)scratch + scratch_bytes) {
+        scd_set_error("scd_fp: scratch too small (%zu bytes given, %zu needed; see scd_fp_scratch_bytes)",
+                      scratch_bytes, c.scratch_bytes + 128);
+        return SCD_E_WORKSPACE;
+    }
+    MqParams P;
+    memset(&P, 0, sizeof(P));
+    P.img = img; P.sino = sino; P.packed = (float *)sp; P.fp = g->d_fp; P.order = g->d_order;
+    P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
+    P.NA = c.NA; P.nbuf = c.nbuf; P.CS = c.CS; P.rows_per_cta = c.rows_per_cta; P.ring_bytes = (int)c.ring_bytes; P.L = c.L;
+    P.need_cls[0] = ncls[0] > 0; P.need_cls[1] = ncls[1] > 0;
+    const unsigned gx = (unsigned)c.groups * c.CS;
+
+    // ---- pack: image -> tile-ready layout (both orientations), producer fused in ----
+    {
+        if (c.groups > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
+        dim3 pg((std::max(g->n1, c.L.rows[1]) + PK_T - 1) / PK_T, (std::max(g->n0, c.L.rows[0]) + PK_T - 1) / PK_T, c.groups);
+        if (Q.mode == 0) fp_packq_kernel<0><<<pg, 256, 0, st>>>(P, Q);
+        else if (Q.mode == 1) fp_packq_kernel<1><<<pg, 256, 0, st>>>(P, Q);
+        else fp_packq_kernel<2><<<pg, 256, 0, st>>>(P, Q);
+        SCD_LAUNCH_CHECK("fp_packq_kernel");
+    }
+
+    const MqPlan pl = mq_plan(g, c, angle_lo, angle_hi);
+    if (pl.units == 0) return 0;
+    if (pl.units > 65535) { scd_set_error("scd_fp: too many angle chunks"); return SCD_E_INVALID; }
+    P.n_runs = pl.n_runs;
+    for (int i = 0; i < pl.n_runs; ++i) P.runs[i] = pl.runs[i];
+    dim3 grid(gx, pl.units);       // x: (group, cluster rank) -- y: unit, largest first
+    int rc = SCD_E_INVALID;
+#define MQ_CASE(VV, LL, TT)                                                                         \
+    if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 16)                                      \
+        rc = c.NSLOT == 6 ? mq_launch_t<VV, LL, 6, TT, 16>(P, grid, c.smem, st)                     \
+                          : mq_launch_t<VV, LL, 13, TT, 16>(P, grid, c.smem, st);
+#define MQ_CASE32(VV, LL, TT)                                                                       \
+    if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 32)                                      \
+        rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, grid, c.smem, st)                     \
+                          : mq_launch_t<VV, LL, 6, TT, 32>(P, grid, c.smem, st);
+    MQ_CASE(1, 1, 8) MQ_CASE(2, 1, 8) MQ_CASE(4, 1, 8) MQ_CASE(4, 1, 4)
+    MQ_CASE(4, 2, 8) MQ_CASE(4, 2, 4) MQ_CASE(4, 4, 4) MQ_CASE(4, 4, 2) MQ_CASE(4, 8, 2)
+    MQ_CASE32(4, 2, 8) MQ_CASE32(4, 2, 4) MQ_CASE32(4, 4, 4) MQ_CASE32(4, 4, 2) MQ_CASE32(4, 8, 2)
+#undef MQ_CASE
+#undef MQ_CASE32
+    if (rc == SCD_E_INVALID) scd_set_error("scd_fp: no kernel for V=%d LPR=%d TR=%d warps=%d", c.V, c.LPR, c.TR, c.NWT);
+    return rc;
+}
+
+// ------------------------------------------------------------ dispatcher ---
+// fp_impl tuning knob: 0 / 4 = this kernel, 3 = the previous generation (fp_joseph.cu), kept for A/B runs
+int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
+                  int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                  const FpPrologue *prologue)
+{
+    if (!g || (!img && !(prologue && prologue->mode != 0)) || !sino) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
+    if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
+        scd_set_error("scd_fp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",
+                      batch, angle_lo, angle_hi, g->n_angles);
+        return SCD_E_INVALID;
+    }
+    if (batch == 0 || angle_lo == angle_hi) return 0;
+    if (g->tune_fp_impl == 3)
+        return scd_launch_fp_v3(g, img, sino, batch, angle_lo, angle_hi, scratch, scratch_bytes, st, prologue);
+    return scd_launch_fp_v4(g, img, sino, batch, angle_lo, angle_hi, scratch, scratch_bytes, st, prologue);
+}
+
+size_t scd_fp_scratch_need(const scd_geom *g, int batch)
+{
+    return std::max(scd_fp_scratch_need_v3(g, batch), scd_fp_scratch_need_v4(g, batch));
+}

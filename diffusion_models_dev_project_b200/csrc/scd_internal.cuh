@@ -57,7 +57,7 @@ struct scd_geom {
     int     *h_order;
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
-    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf;
+    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_impl, tune_fp_plan;
     int tune_bp_samples, tune_bp_tile;
 };
 
@@ -78,6 +78,15 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
                   int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
                   cudaStream_t st, const FpPrologue *prologue = nullptr);
 size_t scd_fp_scratch_need(const scd_geom *g, int batch);
+// the two generations of the projector behind scd_launch_fp (tuning knob fp_impl)
+int scd_launch_fp_v3(const scd_geom *g, const float *img, float *sino, int batch,
+                     int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
+                     cudaStream_t st, const FpPrologue *prologue);
+int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, int batch,
+                     int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
+                     cudaStream_t st, const FpPrologue *prologue);
+size_t scd_fp_scratch_need_v3(const scd_geom *g, int batch);
+size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch);
 
 // Backprojection with fused epilogue:
 //   val  = c_acc*BP + c1*add1 + c2*add2

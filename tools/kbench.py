@@ -48,7 +48,7 @@ def main():
     nbytes = 4 * (a.im * a.im + rt.obs_shape[0] * rt.obs_shape[1]) * a.batch
 
     def run(tune):
-        keys = ['fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'bp_samples', 'bp_tile']
+        keys = ['fp_impl', 'fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'bp_samples', 'bp_tile']
         rt.set_tuning(dev, **{k: tune.get(k, 0) for k in keys})
         if a.kernel == 'fp':
             fn = lambda: rt._fp(x)          # noqa: E731
@@ -65,10 +65,20 @@ def main():
 
     if a.sweep:
         if a.kernel == 'fp':
-            for S, NA, TR, TH, NB in itertools.product([1, 2, 4], [1, 2, 5], [8, 16, 32], [256, 384], [2, 4, 8]):
-                if S > a.batch:
+            run(dict(fp_impl=3))
+            run(dict())
+            sbs = [sb for sb in (4, 8, 16, 32) if sb <= max(4, a.batch)]
+            big = a.batch >= 64
+            for SB, NA, TR, CS, TH, PL in itertools.product(sbs, [2, 3, 4], [2, 4, 8], [1, 2, 4, 8], [512, 1024], [0, 1]):
+                if (SB >= 16 and TR == 8) or (SB == 32 and TR != 2) or (SB <= 8 and TR == 2) or (SB == 4 and TH == 1024):
                     continue
-                run(dict(fp_samples=S, fp_angles=NA, fp_rows=TR, fp_threads=TH, fp_nbuf=NB))
+                if big and (CS > 1 or SB == 4):
+                    continue
+                if not big and PL == 1:
+                    continue
+                if CS > 1 and a.batch // SB * (a.angles // NA) * CS > 1200:
+                    continue
+                run(dict(fp_samples=SB, fp_angles=NA, fp_rows=TR, fp_cluster=CS, fp_threads=TH, fp_plan=PL))
         elif a.kernel == 'bp':
             for S, T in itertools.product([1, 2, 4], [16, 32, 64]):
                 if S > a.batch:
