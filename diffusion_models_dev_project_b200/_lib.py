@@ -33,7 +33,9 @@ SIGNATURES = {
     "scd_geom_destroy": (C.c_int, [C.c_void_p]),
     "scd_fp_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scd_fp": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "scd_bp": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_float, _F, C.c_float, C.c_void_p]),
+    "scd_bp_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "scd_bp": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_float, _F, C.c_float,
+                         C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_cg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scd_cg": (C.c_int, [C.c_void_p, _F, _F, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_tweedie_rhs": (C.c_int, [_F, _F, _F, _F, _F, C.c_int, C.c_double, _F, _F, C.c_int, C.c_int64, C.c_void_p]),

@@ -199,7 +199,7 @@ static BpConfig bp_choose(const scd_geom *g, int batch, int angle_lo, int angle_
     return c;
 }
 
-int scd_bp_ctas_per_sample(const scd_geom *g, int batch)
+int scd_bp_ctas_per_sample_v1(const scd_geom *g, int batch)
 {
     BpConfig c = bp_choose(g, batch, 0, g->n_angles);
     return (int)(c.grid.x * c.grid.y);
@@ -219,8 +219,8 @@ static int bp_launch_t(const BpParams &P, const BpConfig &c, cudaStream_t st)
     return 0;
 }
 
-int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
-                  int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st)
+int scd_launch_bp_v1(const scd_geom *g, const float *sino, float *out, int batch,
+                     int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st)
 {
     if (!g || !sino || !out) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {

@@ -1,0 +1,461 @@
+// K2 (v2)  bp_tile -- pixel-driven linear-interpolation backprojector A*, batched, with the CG
+// axpy and dot product fused into its epilogue.
+//
+// Replaces SimpleTrafo.trafo_adjoint (reference src/physics/trafo.py:61 -> ODL -> ASTRA par_bp),
+// the `x + gamma*A*(A x)` axpy of `op` (src/samplers/utils.py:188-189) and the <p,d> / ||r||^2
+// reductions of cg (src/utils/cg.py:22,27).  Arithmetic: SURVEY.md Appendix A, "A*".
+//
+// Like the forward projector (fp_march.cu) the kernel is bound by the shared-memory pipe (two
+// taps per pixel, angle and sample), so the sinogram is read in a sample-interleaved layout
+//
+//   sino_il[group][angle][NB bins][SB]     SB = V*LPR samples interleaved per bin,
+//                                          PADL zero bins before the detector, zero bins after
+//
+// in which the detector segment a pixel tile projects onto is ONE contiguous, 16-byte aligned
+// byte range per angle: it is staged by cp.async.bulk (TMA unit) into an mbarrier ring of angle
+// chunks by a producer warp.  fp_march writes this layout directly inside the CG solve; user
+// sinograms are converted by sino_pack_kernel first.
+//
+//   CTA     = (32 x TH pixel tile, group of SB samples); 16 marching warps + 1 producer warp
+//   lanes   = LPR consecutive lanes share a pixel, each owns V samples (one LDS.(32V) per tap);
+//             pixels of a warp are adjacent along k1 (the contiguous image axis): taps of
+//             neighbouring pixels are <= 1.01 bins apart -> conflict-free / broadcast
+//   thread  = PPT pixels in a column (k0 .. k0+PPT-1), accumulators in registers
+//   angle range [lo,hi): the angle-sharded variant (multi-GPU config 4) is the same kernel;
+//             partial images are summed by the caller (NCCL).
+#include "scd_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#define BQ_NW        16
+#define BQ_THREADS   (32 * (BQ_NW + 1))
+#define BQ_MAX_NBUF  8
+#define BQ_MAGIC      12582912.0f
+#define BQ_MAGIC_BITS 0x4B400000
+
+struct BqParams {
+    const float   *sino_il;
+    float         *out;
+    const BpAngle *bp;
+    int n0, n1, n_angles, n_det, batch;
+    int angle_lo, angle_hi;
+    int SEG;                 // bins per staged segment (multiple of 4)
+    int AC, nbuf;            // angles per chunk, ring depth
+    int PADL, NB;            // interleaved sinogram row
+    size_t group_floats;     // n_angles * NB * SB
+    BpEpilogue ep;
+};
+
+// ------------------------------------------------------------ sino pack ---
+// user sinogram [B][n_angles][n_det] -> sino_il (angles [lo,hi) only)
+// grid = (bin chunks of 256, angles in range, groups)
+__global__ void __launch_bounds__(256)
+sino_pack_kernel(const float *sino, float *sino_il, int n_angles, int n_det, int batch,
+                 int angle_lo, int SB, int PADL, int NB, size_t group_floats)
+{
+    __shared__ float tile[16][257];
+    const int tid = threadIdx.x;
+    const int J0 = blockIdx.x * 256, a = angle_lo + blockIdx.y, grp = blockIdx.z;
+    const int j = J0 + tid;
+    for (int s = 0; s < SB; ++s) {
+        const int b = grp * SB + s;
+        float v = 0.f;
+        if (b < batch && j >= PADL && j < PADL + n_det)
+            v = __ldg(sino + ((size_t)b * n_angles + a) * n_det + (j - PADL));
+        tile[s][tid] = v;
+    }
+    __syncthreads();
+    float *dst = sino_il + (size_t)grp * group_floats + ((size_t)a * NB + J0) * SB;
+    const int nj = min(256, NB - J0);
+    for (int idx = tid; idx < nj * SB; idx += 256) {
+        const int jj = idx / SB, s = idx - jj * SB;
+        dst[idx] = tile[s][jj];
+    }
+}
+
+// ----------------------------------------------------------------- tile ---
+__device__ __forceinline__ unsigned bq_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bq_mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bq_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bq_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bq_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bq_mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(bq_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bq_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BQ_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BQ_DONE;\n"
+        "bra BQ_WAIT;\n"
+        "BQ_DONE:\n"
+        "}\n" :: "r"(bq_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bq_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bq_smem_u32(bar)) : "memory");
+}
+
+template <int V> struct BqVec;
+template <> struct BqVec<1> {
+    typedef float T;
+    template <int OFF> static __device__ __forceinline__ T ld(unsigned a)
+    { T v; asm volatile("ld.shared.f32 %0, [%1+%2];\n" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
+};
+template <> struct BqVec<2> {
+    typedef float2 T;
+    template <int OFF> static __device__ __forceinline__ T ld(unsigned a)
+    { T v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2+%3];\n" : "=f"(v.x), "=f"(v.y) : "r"(a), "n"(OFF)); return v; }
+};
+template <> struct BqVec<4> {
+    typedef float4 T;
+    template <int OFF> static __device__ __forceinline__ T ld(unsigned a)
+    {
+        T v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF));
+        return v;
+    }
+};
+
+// acc += l*wl + r*w; V >= 2 uses the packed fp32x2 FMA of sm_100 (FFMA2)
+__device__ __forceinline__ void bq_tap(float (&p)[1], float l, float r, float wl, float w)
+{ p[0] = fmaf(r, w, fmaf(l, wl, p[0])); }
+__device__ __forceinline__ void bq_tap(float (&p)[2], float2 l, float2 r, float wl, float w)
+{
+    float2 a = make_float2(p[0], p[1]);
+    a = __ffma2_rn(l, make_float2(wl, wl), a);
+    a = __ffma2_rn(r, make_float2(w, w), a);
+    p[0] = a.x; p[1] = a.y;
+}
+__device__ __forceinline__ void bq_tap(float (&p)[4], float4 l, float4 r, float wl, float w)
+{
+    const float2 wl2 = make_float2(wl, wl), w2 = make_float2(w, w);
+    float2 a = make_float2(p[0], p[1]), b = make_float2(p[2], p[3]);
+    a = __ffma2_rn(make_float2(l.x, l.y), wl2, a);
+    b = __ffma2_rn(make_float2(l.z, l.w), wl2, b);
+    a = __ffma2_rn(make_float2(r.x, r.y), w2, a);
+    b = __ffma2_rn(make_float2(r.z, r.w), w2, b);
+    p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+}
+
+// V samples per lane, LPR lanes per pixel (SB = V*LPR), PPT pixels per thread
+template <int V, int LPR, int PPT>
+__global__ void __launch_bounds__(BQ_THREADS, 2)
+bp_tile_kernel(const BqParams P)
+{
+    typedef BqVec<V> LD;
+    typedef typename LD::T VT;
+    constexpr int SB = V * LPR;
+    constexpr int RPW = 32 / LPR;          // pixels of a warp along k1
+    constexpr int WX = LPR;                // warps along k1 (32 pixels)
+    constexpr int WY = BQ_NW / WX;         // warps along k0
+    constexpr int TH = WY * PPT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K0 = blockIdx.y * TH, K1 = blockIdx.x * 32;
+    const int grp = blockIdx.z, b0 = grp * SB;
+    const int nang = P.angle_hi - P.angle_lo;
+    const int AC = P.AC, NBUF = P.nbuf;
+    const unsigned SEGB = (unsigned)(P.SEG * SB * 4);
+    const int nchunks = (nang + AC - 1) / AC;
+
+    // shared memory: ring[nbuf][AC][SEG*SB] | mbarriers | per-angle constants | dot partials
+    const size_t ring_bytes = (size_t)NBUF * AC * SEGB;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + ring_bytes);
+    unsigned long long *empty = full + BQ_MAX_NBUF;
+    float4 *cst = reinterpret_cast<float4 *>(empty + BQ_MAX_NBUF);
+    float *red = reinterpret_cast<float *>(cst + nang);
+
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) { bq_mbar_init(&full[i], 1); bq_mbar_init(&empty[i], BQ_NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    // ---- per-angle constants re-centred on this tile (fp64): the fp32 index arithmetic then
+    // works on magnitudes < SEG
+    {
+        const int th = min(TH, P.n0 - K0), tw = min(32, P.n1 - K1);
+        for (int i = tid; i < nang; i += BQ_THREADS) {
+            const BpAngle A = P.bp[P.angle_lo + i];
+            const double v00 = A.ci * (double)K0 + A.si * (double)K1 + A.oi;
+            const double vmin = v00 + fmin(0.0, A.ci * (double)(th - 1)) + fmin(0.0, A.si * (double)(tw - 1));
+            int j0 = (int)floor(vmin) - 1;                 // one bin of slack below (fp32 rounding)
+            j0 = ((j0 + P.PADL) & ~3) - P.PADL;            // 16-byte aligned source whatever SB
+            // zf = v - j0 >= 1: floor(zf) = segment index of the left tap
+            cst[i] = make_float4((float)A.ci, (float)A.si, (float)(v00 - (double)j0), __int_as_float(j0));
+        }
+    }
+    __syncthreads();
+
+    float acc[PPT][V];
+#pragma unroll
+    for (int m = 0; m < PPT; ++m)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[m][v] = 0.f;
+
+    const int lr = lane / LPR, lq = lane - lr * LPR;
+    const int wx = warp % WX, wy = warp / WX;
+    const int k1 = K1 + wx * RPW + lr;
+    const int k0b = K0 + wy * PPT;
+
+    if (warp == BQ_NW) {
+        // ------------------------------ producer warp ------------------------------
+        const float *src0 = P.sino_il + (size_t)grp * P.group_floats;
+        const unsigned ring0 = bq_smem_u32(smem_raw);
+        int bi = 0; unsigned ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            if (c >= NBUF) bq_mbar_wait(&empty[bi], ph ^ 1u);
+            const int nac = min(AC, nang - c * AC);
+            if (lane == 0) bq_mbar_expect_tx(&full[bi], (unsigned)nac * SEGB);
+            __syncwarp();
+            for (int i = lane; i < nac; i += 32) {
+                const int ia = c * AC + i;
+                const int j0 = __float_as_int(cst[ia].w);
+                const float *src = src0 + ((size_t)(P.angle_lo + ia) * P.NB + (size_t)(P.PADL + j0)) * SB;
+                bq_bulk_g2s(ring0 + (unsigned)(bi * AC + i) * SEGB, src, SEGB, &full[bi]);
+            }
+            if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+        }
+    } else {
+        // ------------------------------ marching warps -----------------------------
+        // pixels outside the image are computed at the clamped position and never stored
+        const float lxf = (float)(min(k1, P.n1 - 1) - K1);
+        float kyf[PPT];
+#pragma unroll
+        for (int m = 0; m < PPT; ++m) kyf[m] = (float)(min(k0b + m, P.n0 - 1) - K0);
+        const unsigned lane_base = bq_smem_u32(smem_raw) + (unsigned)(lq * V * 4) - (unsigned)BQ_MAGIC_BITS * (unsigned)(SB * 4);
+        const unsigned cst_base = bq_smem_u32(cst);
+        int bi = 0; unsigned ph = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            bq_mbar_wait(&full[bi], ph);
+            const int nac = min(AC, nang - c * AC);
+            unsigned seg = lane_base + (unsigned)(bi * AC) * SEGB;
+            unsigned ca = cst_base + (unsigned)(c * AC) * 16u;
+#pragma unroll 2
+            for (int i = 0; i < nac; ++i, seg += SEGB, ca += 16u) {
+                const float4 cs = BqVec<4>::ld<0>(ca);
+                const float vb = fmaf(lxf, cs.y, cs.z);
+                float w[PPT];
+                unsigned ad[PPT];
+#pragma unroll
+                for (int m = 0; m < PPT; ++m) {
+                    const float z = fmaf(kyf[m], cs.x, vb);
+                    const float t = __fadd_rd(z, BQ_MAGIC);                 // floor(z) in the mantissa
+                    w[m] = z - (t - BQ_MAGIC);
+                    ad[m] = seg + (unsigned)__float_as_int(t) * (unsigned)(SB * 4);
+                }
+                VT tl[PPT], tr[PPT];
+#pragma unroll
+                for (int m = 0; m < PPT; ++m) {
+                    tl[m] = LD::template ld<0>(ad[m]);
+                    tr[m] = LD::template ld<SB * 4>(ad[m]);
+                }
+#pragma unroll
+                for (int m = 0; m < PPT; ++m) bq_tap(acc[m], tl[m], tr[m], 1.0f - w[m], w[m]);
+            }
+            __syncwarp();
+            if (lane == 0) bq_mbar_arrive(&empty[bi]);
+            if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+        }
+    }
+
+    // ---- epilogue: axpy, second output, dot-product partials ---------------
+    const BpEpilogue &E = P.ep;
+    float dsum[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) dsum[v] = 0.f;
+    if (warp < BQ_NW && k1 < P.n1) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int b = b0 + lq * V + v;
+            if (b >= P.batch) continue;
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) {
+                const int k0 = k0b + m;
+                if (k0 < P.n0) {
+                    const size_t o = ((size_t)b * P.n0 + k0) * P.n1 + k1;
+                    float val = E.c_acc * acc[m][v];
+                    float a1 = 0.f;
+                    if (E.add1) { a1 = E.add1[o]; val = fmaf(E.c1, a1, val); }
+                    if (E.add2) val = fmaf(E.c2, E.add2[o], val);
+                    P.out[o] = val;
+                    if (E.out2) E.out2[o] = val;
+                    dsum[v] += val * (E.dot_with_add1 ? a1 : val);
+                }
+            }
+        }
+    }
+    if (E.dot_part) {
+        // lanes with equal lq hold the same samples: add over the pixels of the warp, then over warps
+        if (warp < BQ_NW) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                float s = dsum[v];
+#pragma unroll
+                for (int off = 16; off >= LPR; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (lr == 0) red[warp * SB + lq * V + v] = s;
+            }
+        }
+        __syncthreads();
+        if (tid < SB) {
+            const int b = b0 + tid;
+            if (b < P.batch) {
+                float s = 0.f;
+                for (int w = 0; w < BQ_NW; ++w) s += red[w * SB + tid];
+                E.dot_part[(size_t)b * E.dot_stride + blockIdx.y * gridDim.x + blockIdx.x] = s;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------- host side ---
+struct BqConfig { int V, LPR, SB, PPT, TH, SEG, AC, nbuf; size_t smem; dim3 grid; };
+
+static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_hi)
+{
+    BqConfig c;
+    c.SB = scd_group_samples(g, batch);
+    c.V = c.SB >= 4 ? 4 : c.SB;
+    c.LPR = c.SB / c.V;
+    const int WY = BQ_NW / c.LPR;
+    // tile height 16 or 32 rows: 16 unless that makes more than ~16 CTAs per SM
+    const int groups = (batch + c.SB - 1) / c.SB;
+    int th = 16;
+    const long tiles16 = (long)((g->n1 + 31) / 32) * ((g->n0 + 15) / 16) * groups;
+    if (tiles16 > 16L * g->sm_count) th = 32;
+    if (g->tune_bp_tile == 16 || g->tune_bp_tile == 32) th = g->tune_bp_tile;
+    if (c.LPR == 4) th = 16;                   // 8 pixels x 4 samples per thread would not fit two CTAs per SM
+    c.PPT = th / WY; c.TH = th;
+    double span = 0.0;
+    for (int i = angle_lo; i < angle_hi; ++i)
+        span = std::max(span, std::fabs(g->h_bp[i].ci) * (th - 1) + std::fabs(g->h_bp[i].si) * 31.0);
+    c.SEG = (((int)std::ceil(span) + 9) + 3) & ~3;
+    const int nang = std::max(1, angle_hi - angle_lo);
+    const size_t segb = (size_t)c.SEG * c.SB * 4;
+    // chunks of ~28 KB, ring of ~90 KB (two CTAs per SM)
+    c.AC = (int)std::max<size_t>(2, std::min<size_t>(32, (28 * 1024) / segb));
+    c.AC = std::min(c.AC, nang);
+    const int nchunks = (nang + c.AC - 1) / c.AC;
+    c.nbuf = (int)std::max<size_t>(2, std::min<size_t>(BQ_MAX_NBUF, (90 * 1024) / (c.AC * segb)));
+    c.nbuf = std::max(1, std::min(c.nbuf, nchunks));
+    c.smem = (size_t)c.nbuf * c.AC * segb + 2 * BQ_MAX_NBUF * 8 + (size_t)nang * 16 + (size_t)BQ_NW * c.SB * 4 + 64;
+    c.grid = dim3((g->n1 + 31) / 32, (g->n0 + th - 1) / th, groups);
+    return c;
+}
+
+int scd_bp_ctas_per_sample_v2(const scd_geom *g, int batch)
+{
+    BqConfig c = bq_choose(g, batch, 0, g->n_angles);
+    return (int)(c.grid.x * c.grid.y);
+}
+
+size_t scd_sino_il_bytes(const scd_geom *g, int batch)
+{
+    if (!g || batch <= 0) return 0;
+    // the group size may be overridden by tuning: size for the worst case
+    size_t need = 0;
+    for (int SB = 1; SB <= 16; SB <<= 1)
+        need = std::max(need, (size_t)((batch + SB - 1) / SB) * g->n_angles * g->il_nb * SB * 4);
+    return need + 256;
+}
+
+template <int V, int LPR, int PPT>
+static int bq_launch_t(const BqParams &P, const BqConfig &c, cudaStream_t st)
+{
+    static int configured_smem = -1;
+    if ((int)c.smem > configured_smem) {
+        SCD_CUDA(cudaFuncSetAttribute(bp_tile_kernel<V, LPR, PPT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        configured_smem = (int)c.smem;
+    }
+    bp_tile_kernel<V, LPR, PPT><<<c.grid, BQ_THREADS, c.smem, st>>>(P);
+    SCD_LAUNCH_CHECK("bp_tile_kernel");
+    return 0;
+}
+
+int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int batch,
+                     int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st)
+{
+    if (!g || !sino_il || !out) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
+    if (batch <= 0) return 0;
+    BqConfig c = bq_choose(g, batch, angle_lo, angle_hi);
+    if (c.grid.z > 65535) { scd_set_error("scd_bp: batch too large"); return SCD_E_INVALID; }
+    if (c.smem > (size_t)g->smem_optin) { scd_set_error("scd_bp: angle table does not fit in shared memory"); return SCD_E_INVALID; }
+    BqParams P;
+    memset(&P, 0, sizeof(P));
+    P.sino_il = sino_il; P.out = out; P.bp = g->d_bp;
+    P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
+    P.angle_lo = angle_lo; P.angle_hi = angle_hi; P.SEG = c.SEG; P.AC = c.AC; P.nbuf = c.nbuf;
+    P.PADL = g->il_padl; P.NB = g->il_nb; P.group_floats = (size_t)g->n_angles * g->il_nb * c.SB;
+    P.ep = ep;
+    const int WY = BQ_NW / c.LPR;
+    (void)WY;
+#define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st);
+    BQ_CASE(1, 1, 1) BQ_CASE(1, 1, 2) BQ_CASE(2, 1, 1) BQ_CASE(2, 1, 2) BQ_CASE(4, 1, 1) BQ_CASE(4, 1, 2)
+    BQ_CASE(4, 2, 2) BQ_CASE(4, 2, 4) BQ_CASE(4, 4, 4)
+#undef BQ_CASE
+    scd_set_error("scd_bp: unsupported config V=%d LPR=%d PPT=%d", c.V, c.LPR, c.PPT);
+    return SCD_E_INVALID;
+}
+
+int scd_launch_sino_pack(const scd_geom *g, const float *sino, float *sino_il, int batch,
+                         int angle_lo, int angle_hi, cudaStream_t st)
+{
+    if (batch <= 0 || angle_hi <= angle_lo) return 0;
+    const int SB = scd_group_samples(g, batch);
+    const int groups = (batch + SB - 1) / SB;
+    dim3 grid((g->il_nb + 255) / 256, angle_hi - angle_lo, groups);
+    if (grid.y > 65535 || grid.z > 65535) { scd_set_error("scd_bp: too many angles / samples"); return SCD_E_INVALID; }
+    sino_pack_kernel<<<grid, 256, 0, st>>>(sino, sino_il, g->n_angles, g->n_det, batch, angle_lo, SB,
+                                           g->il_padl, g->il_nb, (size_t)g->n_angles * g->il_nb * SB);
+    SCD_LAUNCH_CHECK("sino_pack_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------ dispatcher ---
+// bp_impl tuning knob: 0 / 2 = this kernel, 1 = the previous generation (bp_pixel.cu), kept for A/B runs
+int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
+                  int angle_lo, int angle_hi, const BpEpilogue &ep, void *scratch, size_t scratch_bytes,
+                  cudaStream_t st)
+{
+    if (!g || !sino || !out) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
+    if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
+        scd_set_error("scd_bp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",
+                      batch, angle_lo, angle_hi, g->n_angles);
+        return SCD_E_INVALID;
+    }
+    if (batch == 0) return 0;
+    if (g->tune_bp_impl == 1) return scd_launch_bp_v1(g, sino, out, batch, angle_lo, angle_hi, ep, st);
+    const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
+    const size_t need = scd_sino_il_bytes(g, batch) - 256;
+    if (!scratch || sp + need > (uintptr_t)scratch + scratch_bytes) {
+        scd_set_error("scd_bp: scratch too small (%zu bytes given, %zu needed; see scd_bp_scratch_bytes)",
+                      scratch_bytes, need + 256);
+        return SCD_E_WORKSPACE;
+    }
+    int rc = scd_launch_sino_pack(g, sino, (float *)sp, batch, angle_lo, angle_hi, st);
+    if (rc) return rc;
+    return scd_launch_bp_il(g, (const float *)sp, out, batch, angle_lo, angle_hi, ep, st);
+}
+
+int scd_bp_ctas_per_sample(const scd_geom *g, int batch)
+{
+    return g->tune_bp_impl == 1 ? scd_bp_ctas_per_sample_v1(g, batch) : scd_bp_ctas_per_sample_v2(g, batch);
+}
+
+int scd_bp_ctas_per_sample_max(const scd_geom *g, int batch)
+{
+    // workspace sizing: independent of the tuning knobs
+    int n = scd_bp_ctas_per_sample_v1(g, batch);
+    n = std::max(n, ((g->n1 + 31) / 32) * ((g->n0 + 15) / 16));
+    return n;
+}

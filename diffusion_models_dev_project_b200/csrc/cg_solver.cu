@@ -25,11 +25,13 @@ static CgLayout cg_layout(const scd_geom *g, int batch)
     CgLayout L;
     L.img = (size_t)g->n0 * g->n1;
     L.sino = (size_t)g->n_angles * g->n_det;
-    const int nbp = scd_bp_ctas_per_sample(g, batch);
+    const int nbp = scd_bp_ctas_per_sample_max(g, batch);
     const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
     L.part_stride = (size_t)std::max(nbp, nvec);
     size_t o = 0;
-    L.off_q = o;  o += align256(L.sino * batch * 4);
+    // q = A p lives in the sample-interleaved layout the backprojector stages from (or in the
+    // user layout when the previous-generation backprojector is selected): room for either
+    L.off_q = o;  o += align256(std::max(L.sino * batch * 4, scd_sino_il_bytes(g, batch)));
     L.off_r = o;  o += align256(L.img * batch * 4);
     L.off_p = o;  o += align256(L.img * batch * 4);
     L.off_d = o;  o += align256(L.img * batch * 4);
@@ -72,14 +74,20 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
     const float gs = gamma * (float)g->adj_scale;
     int rc;
+    const bool il = g->tune_bp_impl != 1;          // q in the interleaved layout
+    float *q_user = il ? nullptr : q, *q_il = il ? q : nullptr;
+    auto bp = [&](float *out, const BpEpilogue &e) {
+        return il ? scd_launch_bp_il(g, q, out, batch, 0, g->n_angles, e, st)
+                  : scd_launch_bp_v1(g, q, out, batch, 0, g->n_angles, e, st);
+    };
 
     // r = rhs - x - gamma A*(A x);  p = r;  rr = ||r||^2
     // (the Tweedie step that produces x_in and rhs may be fused into this projection's pack pass)
-    if ((rc = scd_launch_fp(g, x_in, q, batch, 0, g->n_angles, pack, L.pack_bytes, st, first))) return rc;
+    if ((rc = scd_launch_fp(g, x_in, q_user, q_il, batch, 0, g->n_angles, pack, L.pack_bytes, st, first))) return rc;
     BpEpilogue e0;
     e0.c_acc = -gs; e0.add1 = x_in; e0.c1 = -1.f; e0.add2 = rhs; e0.c2 = 1.f;
     e0.out2 = p; e0.dot_part = rr_a; e0.dot_stride = ps; e0.dot_with_add1 = 0;
-    if ((rc = scd_launch_bp(g, q, r, batch, 0, g->n_angles, e0, st))) return rc;
+    if ((rc = bp(r, e0))) return rc;
     float *rr_old = rr_a, *rr_new = rr_b;
     int rr_old_n = nbp, rr_prev_n = nbp;
 
@@ -93,11 +101,11 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
             up.rr_old_part = rr_new; up.rr_old_n = rr_prev_n;       // and the one before it
             up.part_stride = ps;
         }
-        if ((rc = scd_launch_fp(g, p, q, batch, 0, g->n_angles, pack, L.pack_bytes, st, it > 0 ? &up : nullptr))) return rc;
+        if ((rc = scd_launch_fp(g, p, q_user, q_il, batch, 0, g->n_angles, pack, L.pack_bytes, st, it > 0 ? &up : nullptr))) return rc;
         BpEpilogue e1;
         e1.c_acc = gs; e1.add1 = p; e1.c1 = 1.f; e1.add2 = nullptr; e1.c2 = 0.f;
         e1.out2 = nullptr; e1.dot_part = pd; e1.dot_stride = ps; e1.dot_with_add1 = 1;
-        if ((rc = scd_launch_bp(g, q, d, batch, 0, g->n_angles, e1, st))) return rc;
+        if ((rc = bp(d, e1))) return rc;
         // the first update reads the start iterate and writes the result buffer
         if ((rc = scd_launch_cg_update_xr(it == 0 ? x_in : x, x, r, p, d, rr_old, rr_old_n, pd, nbp, ps, rr_new,
                                           batch, (int64_t)L.img, st))) return rc;
@@ -124,17 +132,22 @@ extern "C" size_t scd_fp_scratch_bytes(const scd_geom_t *g, int batch)
 extern "C" int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
                       int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, void *stream)
 {
-    return scd_launch_fp(g, img, sino, batch, angle_lo, angle_hi, scratch, scratch_bytes, (cudaStream_t)stream);
+    return scd_launch_fp(g, img, sino, nullptr, batch, angle_lo, angle_hi, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t scd_bp_scratch_bytes(const scd_geom_t *g, int batch)
+{
+    return scd_sino_il_bytes(g, batch);
 }
 
 extern "C" int scd_bp(const scd_geom_t *g, const float *sino, float *out, int batch,
                       int angle_lo, int angle_hi, float c_acc, const float *addend, float c_add,
-                      void *stream)
+                      void *scratch, size_t scratch_bytes, void *stream)
 {
     BpEpilogue e;
     e.c_acc = c_acc; e.add1 = addend; e.c1 = c_add; e.add2 = nullptr; e.c2 = 0.f;
     e.out2 = nullptr; e.dot_part = nullptr; e.dot_stride = 0; e.dot_with_add1 = 0;
-    return scd_launch_bp(g, sino, out, batch, angle_lo, angle_hi, e, (cudaStream_t)stream);
+    return scd_launch_bp(g, sino, out, batch, angle_lo, angle_hi, e, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int scd_tweedie_rhs(const float *x, const float *s, const float *atb, const float *t,
@@ -201,7 +214,7 @@ static int host_roundtrip(const scd_geom_t *g, const float *in_host, size_t in_e
     if (batch <= 0) return 0;
     float *d_in = nullptr, *d_out = nullptr;
     void *d_scr = nullptr;
-    const size_t scr_bytes = forward ? scd_fp_scratch_need(g, batch) : 0;
+    const size_t scr_bytes = forward ? scd_fp_scratch_need(g, batch) : scd_sino_il_bytes(g, batch);
     cudaStream_t st = nullptr;
     int rc = 0;
     cudaError_t e;
@@ -209,9 +222,9 @@ static int host_roundtrip(const scd_geom_t *g, const float *in_host, size_t in_e
     if ((e = cudaMalloc(&d_in, in_elems * 4)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
     if ((e = cudaMalloc(&d_out, out_elems * 4)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
     if ((e = cudaMemcpyAsync(d_in, in_host, in_elems * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) { rc = scd_cuda_fail(e, "H2D"); goto done; }
-    if (forward && (e = cudaMalloc(&d_scr, scr_bytes)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
+    if ((e = cudaMalloc(&d_scr, scr_bytes)) != cudaSuccess) { rc = scd_cuda_fail(e, "cudaMalloc"); goto done; }
     if (forward) rc = scd_fp(g, d_in, d_out, batch, 0, g->n_angles, d_scr, scr_bytes, st);
-    else rc = scd_bp(g, d_in, d_out, batch, 0, g->n_angles, (float)g->adj_scale, nullptr, 0.f, st);
+    else rc = scd_bp(g, d_in, d_out, batch, 0, g->n_angles, (float)g->adj_scale, nullptr, 0.f, d_scr, scr_bytes, st);
     if (rc) goto done;
     if ((e = cudaMemcpyAsync(out_host, d_out, out_elems * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) { rc = scd_cuda_fail(e, "D2H"); goto done; }
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) { rc = scd_cuda_fail(e, "sync"); goto done; }

@@ -12,9 +12,8 @@
 //                 SB = V*LPR samples interleaved per pixel; class 1 is the transposed image so
 //                 the march is class-agnostic; 1 zero pixel left, 2 right, rows padded to x8.
 //   lanes         LPR consecutive lanes share one ray, each owns V samples (one LDS.(32V) per
-//                 tap).  With SB = 32 a quarter-warp reads exactly one pixel = one 128 B
-//                 wavefront whatever the ray spacing; SB = 16 conflicts only when neighbouring
-//                 rays are two pixels apart.
+//                 tap).  With SB = 16 a quarter-warp reads two pixels of 64 B: it conflicts only
+//                 when neighbouring rays are two pixels apart (9 % of the wavefronts at 256^2).
 //   warp          a "chunk" of RPW = 32/LPR adjacent rays; chunks of the NA angles of the CTA
 //                 are dealt round-robin to the 15 marching warps (NSLOT chunks per warp).  A
 //                 chunk whose rays all miss the image in a strip is skipped (warp vote).
@@ -52,7 +51,8 @@ struct MqLayout {
 
 struct MqParams {
     const float   *img;
-    float         *sino;
+    float         *sino;     // user layout [batch][n_angles][n_det] or NULL
+    float         *sino_il;  // interleaved layout [group][n_angles][il_nb][SB] (bp_tile.cu) or NULL
     float         *packed;
     const FpAngle *fp;
     const int     *order;
@@ -62,6 +62,7 @@ struct MqParams {
     int CS;                  // cluster size = row split
     int rows_per_cta;        // multiple of 8
     int ring_bytes;          // strip ring (aliased by the partial sums), tables follow
+    int il_padl, il_nb;      // interleaved sinogram row: zero bins before / total bins
     int need_cls[2];
     MqLayout L;
     int n_runs;
@@ -432,18 +433,45 @@ fp_march_kernel(const MqParams P)
     const int e_lo = rank * per, e_hi = min(E, e_lo + per);
     const int cnt = max(e_hi - e_lo, 0);
     const size_t sino_sz = (size_t)P.n_angles * n_det;
-    for (int idx = tid; idx < cnt * SB; idx += NTHR) {
-        const int s = idx / cnt, e = e_lo + (idx - s * cnt);
-        float v;
-        if (CS > 1) {
-            v = 0.f;
-            for (int r = 0; r < CS; ++r) v += cluster.map_shared_rank(red, r)[(size_t)s * E + e];
-        } else {
-            v = red[(size_t)s * E + e];
+    if (P.sino) {
+        for (int idx = tid; idx < cnt * SB; idx += NTHR) {
+            const int s = idx / cnt, e = e_lo + (idx - s * cnt);
+            float v;
+            if (CS > 1) {
+                v = 0.f;
+                for (int r = 0; r < CS; ++r) v += cluster.map_shared_rank(red, r)[(size_t)s * E + e];
+            } else {
+                v = red[(size_t)s * E + e];
+            }
+            if (b0 + s < P.batch) {
+                const int ai = e / n_det, j = e - ai * n_det;
+                P.sino[(size_t)(b0 + s) * sino_sz + (size_t)ang[ai].id * n_det + j] = v * ang[ai].scale;
+            }
         }
-        if (b0 + s < P.batch) {
+    }
+    if (P.sino_il) {
+        // interleaved rows for the backprojector: samples fastest, zero bins either side
+        float *dst = P.sino_il + (size_t)grp * ((size_t)P.n_angles * P.il_nb * SB);
+        for (int idx = tid; idx < cnt * SB; idx += NTHR) {
+            const int el = idx / SB, s = idx - el * SB, e = e_lo + el;
+            float v;
+            if (CS > 1) {
+                v = 0.f;
+                for (int r = 0; r < CS; ++r) v += cluster.map_shared_rank(red, r)[(size_t)s * E + e];
+            } else {
+                v = red[(size_t)s * E + e];
+            }
             const int ai = e / n_det, j = e - ai * n_det;
-            P.sino[(size_t)(b0 + s) * sino_sz + (size_t)ang[ai].id * n_det + j] = v * ang[ai].scale;
+            dst[((size_t)ang[ai].id * P.il_nb + P.il_padl + j) * SB + s] = v * ang[ai].scale;
+        }
+        const int npad = P.il_nb - n_det;
+        for (int ai = rank; ai < na; ai += CS) {
+            float *row = dst + (size_t)ang[ai].id * P.il_nb * SB;
+            for (int idx = tid; idx < npad * SB; idx += NTHR) {
+                const int jp = idx / SB, s = idx - jp * SB;
+                const int j = jp < P.il_padl ? jp : n_det + jp;
+                row[(size_t)j * SB + s] = 0.f;
+            }
         }
     }
     if (CS > 1) cluster.sync();                   // keep red alive until every rank has read it
@@ -482,8 +510,7 @@ static bool mq_have_tr(int V, int LPR, int TR)
 {
     if (LPR == 1) return TR == 8 || (V == 4 && TR == 4);
     if (LPR == 2) return TR == 8 || TR == 4;
-    if (LPR == 4) return TR == 4 || TR == 2;
-    return TR == 2;                                // LPR == 8
+    return TR == 4 || TR == 2;                     // LPR == 4
 }
 
 // slot counts instantiated per CTA shape: 16 warps (15 marching, 128 registers) / 32 warps (31 marching, 64 registers)
@@ -493,30 +520,31 @@ static int mq_nslot(int nwt, int need)
     return need <= 3 ? 3 : (need <= 6 ? 6 : 0);
 }
 
+// Samples interleaved per pixel (packed image) and per detector bin (interleaved sinogram): one
+// lane carries up to 4 samples, up to 4 lanes share a ray / pixel.
+int scd_group_samples(const scd_geom *g, int batch)
+{
+    int sb = batch <= 1 ? 1 : (batch == 2 ? 2 : (batch <= 4 ? 4 : (batch <= 8 ? 8 : 16)));
+    const int t = g->tune_fp_samples;
+    if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16) sb = t;
+    // two strips of the thinnest kind must fit next to the tables, else fewer samples per group
+    const int maxpitch = std::max(g->n0, g->n1) + 3;
+    while (sb > 1) {
+        const int trmin = sb >= 16 ? 2 : (sb >= 4 ? 4 : 8);
+        if (2 * (size_t)trmin * maxpitch * sb * 4 + mq_fixed_smem(g, 1) <= (size_t)g->smem_optin) break;
+        sb >>= 1;
+    }
+    return sb;
+}
+
 static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
 {
     MqConfig c;
-    // samples per group: one lane carries up to 4 samples, up to 8 lanes share a ray
-    if (batch <= 1) { c.V = 1; c.LPR = 1; }
-    else if (batch == 2) { c.V = 2; c.LPR = 1; }
-    else if (batch <= 4) { c.V = 4; c.LPR = 1; }
-    else if (batch <= 8) { c.V = 4; c.LPR = 2; }
-    else { c.V = 4; c.LPR = 4; }
-    if (g->tune_fp_samples) {
-        const int sb = g->tune_fp_samples;
-        if (sb == 1) { c.V = 1; c.LPR = 1; } else if (sb == 2) { c.V = 2; c.LPR = 1; }
-        else if (sb == 4) { c.V = 4; c.LPR = 1; } else if (sb == 8) { c.V = 4; c.LPR = 2; }
-        else if (sb == 16) { c.V = 4; c.LPR = 4; } else if (sb == 32) { c.V = 4; c.LPR = 8; }
-    }
+    c.SB = scd_group_samples(g, batch);
+    c.V = c.SB >= 4 ? 4 : c.SB;
+    c.LPR = c.SB / c.V;
     const int maxpitch = std::max(g->n0, g->n1) + 3;
     const size_t budget = (size_t)g->smem_optin;
-    // two strips of the thinnest kind must fit next to the tables, else fewer samples per group
-    for (;;) {
-        c.SB = c.V * c.LPR;
-        const int trmin = c.LPR >= 4 ? 2 : (c.LPR == 2 || c.V == 4 ? 4 : 8);
-        if (2 * (size_t)trmin * maxpitch * c.SB * 4 + mq_fixed_smem(g, 1) <= budget) break;
-        if (c.LPR > 1) c.LPR >>= 1; else if (c.V > 1) c.V >>= 1; else break;
-    }
     c.SB = c.V * c.LPR;
     c.groups = (batch + c.SB - 1) / c.SB;
     const int RPW = 32 / c.LPR;
@@ -664,7 +692,7 @@ size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch)
 {
     if (!g || batch <= 0) return 0;
     size_t need = 0;
-    for (int SB = 1; SB <= 32; SB <<= 1) {
+    for (int SB = 1; SB <= 16; SB <<= 1) {
         const MqLayout L = mq_layout(g, SB);
         need = std::max(need, (size_t)((batch + SB - 1) / SB) * L.group_floats * 4);
     }
@@ -692,7 +720,7 @@ static int mq_launch_t(const MqParams &P, dim3 grid, size_t smem, cudaStream_t s
     return 0;
 }
 
-int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, int batch,
+int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
                      int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
                      const FpPrologue *prologue)
 {
@@ -711,7 +739,7 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, int batch
     }
     MqParams P;
     memset(&P, 0, sizeof(P));
-    P.img = img; P.sino = sino; P.packed = (float *)sp; P.fp = g->d_fp; P.order = g->d_order;
+    P.img = img; P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb; P.packed = (float *)sp; P.fp = g->d_fp; P.order = g->d_order;
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
     P.NA = c.NA; P.nbuf = c.nbuf; P.CS = c.CS; P.rows_per_cta = c.rows_per_cta; P.ring_bytes = (int)c.ring_bytes; P.L = c.L;
     P.need_cls[0] = ncls[0] > 0; P.need_cls[1] = ncls[1] > 0;
@@ -743,33 +771,30 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, int batch
         rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, grid, c.smem, st)                     \
                           : mq_launch_t<VV, LL, 6, TT, 32>(P, grid, c.smem, st);
     MQ_CASE(1, 1, 8) MQ_CASE(2, 1, 8) MQ_CASE(4, 1, 8) MQ_CASE(4, 1, 4)
-    MQ_CASE(4, 2, 8) MQ_CASE(4, 2, 4) MQ_CASE(4, 4, 4) MQ_CASE(4, 4, 2) MQ_CASE(4, 8, 2)
-    MQ_CASE32(4, 2, 8) MQ_CASE32(4, 2, 4) MQ_CASE32(4, 4, 4) MQ_CASE32(4, 4, 2) MQ_CASE32(4, 8, 2)
+    MQ_CASE(4, 2, 8) MQ_CASE(4, 2, 4) MQ_CASE(4, 4, 4) MQ_CASE(4, 4, 2)
+    MQ_CASE32(4, 2, 8) MQ_CASE32(4, 2, 4) MQ_CASE32(4, 4, 4) MQ_CASE32(4, 4, 2)
 #undef MQ_CASE
 #undef MQ_CASE32
     if (rc == SCD_E_INVALID) scd_set_error("scd_fp: no kernel for V=%d LPR=%d TR=%d warps=%d", c.V, c.LPR, c.TR, c.NWT);
     return rc;
 }
 
-// ------------------------------------------------------------ dispatcher ---
-// fp_impl tuning knob: 0 / 4 = this kernel, 3 = the previous generation (fp_joseph.cu), kept for A/B runs
-int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
+// ------------------------------------------------------------- entry point ---
+int scd_launch_fp(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
                   int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
                   const FpPrologue *prologue)
 {
-    if (!g || (!img && !(prologue && prologue->mode != 0)) || !sino) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
+    if (!g || (!img && !(prologue && prologue->mode != 0)) || (!sino && !sino_il)) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
         scd_set_error("scd_fp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",
                       batch, angle_lo, angle_hi, g->n_angles);
         return SCD_E_INVALID;
     }
     if (batch == 0 || angle_lo == angle_hi) return 0;
-    if (g->tune_fp_impl == 3)
-        return scd_launch_fp_v3(g, img, sino, batch, angle_lo, angle_hi, scratch, scratch_bytes, st, prologue);
-    return scd_launch_fp_v4(g, img, sino, batch, angle_lo, angle_hi, scratch, scratch_bytes, st, prologue);
+    return scd_launch_fp_v4(g, img, sino, sino_il, batch, angle_lo, angle_hi, scratch, scratch_bytes, st, prologue);
 }
 
 size_t scd_fp_scratch_need(const scd_geom *g, int batch)
 {
-    return std::max(scd_fp_scratch_need_v3(g, batch), scd_fp_scratch_need_v4(g, batch));
+    return scd_fp_scratch_need_v4(g, batch);
 }

@@ -105,6 +105,20 @@ extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
         b.si = d->dx * sn / d->ds;
         b.oi = ((d->x_min + 0.5 * d->dx) * cs + (d->y_min + 0.5 * d->dx) * sn - d->s_min) / d->ds - 0.5;
     }
+    {
+        // extreme detector coordinates (bin units) of the image corners over all angles -> zero
+        // bins either side of the interleaved sinogram rows so that every staged segment of
+        // bp_tile (start rounded down to x4, up to 12 bins of slack) stays inside its row
+        double vmin = 0.0, vmax = (double)(d->n_det - 1);
+        for (int i = 0; i < na; ++i)
+            for (int c = 0; c < 4; ++c) {
+                const double k0 = (c & 1) ? d->n0 - 1 : 0, k1 = (c & 2) ? d->n1 - 1 : 0;
+                const double v = g->h_bp[i].ci * k0 + g->h_bp[i].si * k1 + g->h_bp[i].oi;
+                vmin = std::min(vmin, v); vmax = std::max(vmax, v);
+            }
+        g->il_padl = ((int)std::max(0.0, 4.0 - std::floor(vmin)) + 3) & ~3;
+        g->il_nb = (g->il_padl + std::max(d->n_det, (int)std::ceil(vmax) + 1) + 13 + 3) & ~3;
+    }
     g->n_cls0 = (int)c0.size();
     std::copy(c0.begin(), c0.end(), g->h_order);
     std::copy(c1.begin(), c1.end(), g->h_order + c0.size());
@@ -158,6 +172,7 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_plan")) g->tune_fp_plan = value;
     else if (!strcmp(key, "bp_samples")) g->tune_bp_samples = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
+    else if (!strcmp(key, "bp_impl")) g->tune_bp_impl = value;
     else { scd_set_error("scd_set_tuning: unknown key '%s'", key); return SCD_E_INVALID; }
     return 0;
 }

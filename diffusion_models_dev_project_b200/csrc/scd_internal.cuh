@@ -58,7 +58,9 @@ struct scd_geom {
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
     int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_impl, tune_fp_plan;
-    int tune_bp_samples, tune_bp_tile;
+    int tune_bp_samples, tune_bp_tile, tune_bp_impl;
+    // sample-interleaved sinogram rows (bp_tile.cu): il_padl zero bins, n_det bins, zero bins up to il_nb
+    int il_padl, il_nb;
 };
 
 // ------------------------------------------------------------ launchers ----
@@ -74,18 +76,17 @@ struct FpPrologue {
     const float *x, *s, *atb, *t, *abar; int n_table; float gamma;
     float *xhat0, *b;
 };
-int scd_launch_fp(const scd_geom *g, const float *img, float *sino, int batch,
+// sino: user layout [batch][n_angles][n_det] (may be NULL); sino_il: sample-interleaved layout read
+// by scd_launch_bp_il (may be NULL)
+int scd_launch_fp(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
                   int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
                   cudaStream_t st, const FpPrologue *prologue = nullptr);
+// samples interleaved per pixel / detector bin for this batch (1, 2, 4, 8 or 16)
+int scd_group_samples(const scd_geom *g, int batch);
 size_t scd_fp_scratch_need(const scd_geom *g, int batch);
-// the two generations of the projector behind scd_launch_fp (tuning knob fp_impl)
-int scd_launch_fp_v3(const scd_geom *g, const float *img, float *sino, int batch,
+int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
                      int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
                      cudaStream_t st, const FpPrologue *prologue);
-int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, int batch,
-                     int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
-                     cudaStream_t st, const FpPrologue *prologue);
-size_t scd_fp_scratch_need_v3(const scd_geom *g, int batch);
 size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch);
 
 // Backprojection with fused epilogue:
@@ -100,11 +101,23 @@ struct BpEpilogue {
     float *out2;
     float *dot_part; int dot_stride; int dot_with_add1;
 };
+// sino in user layout; scratch (>= scd_sino_il_bytes) receives the interleaved copy
 int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
-                  int angle_lo, int angle_hi, const BpEpilogue &ep,
+                  int angle_lo, int angle_hi, const BpEpilogue &ep, void *scratch, size_t scratch_bytes,
                   cudaStream_t st);
-// number of dot_part entries per sample the BP launch for this batch writes
+int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int batch,
+                     int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st);
+int scd_launch_bp_v1(const scd_geom *g, const float *sino, float *out, int batch,
+                     int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st);
+int scd_launch_sino_pack(const scd_geom *g, const float *sino, float *sino_il, int batch,
+                         int angle_lo, int angle_hi, cudaStream_t st);
+size_t scd_sino_il_bytes(const scd_geom *g, int batch);
+// number of dot_part entries per sample the BP launch for this batch writes (current tuning) /
+// an upper bound independent of the tuning (workspace sizing)
 int scd_bp_ctas_per_sample(const scd_geom *g, int batch);
+int scd_bp_ctas_per_sample_max(const scd_geom *g, int batch);
+int scd_bp_ctas_per_sample_v1(const scd_geom *g, int batch);
+int scd_bp_ctas_per_sample_v2(const scd_geom *g, int batch);
 
 // Vector kernels of the CG recurrences (vec_ops.cu).  *_part arrays hold
 // per-block partial sums [batch][part_stride]; consumers add them in index

@@ -189,6 +189,17 @@ class B200RayTrafo(BaseRayTrafo):
             self._work[key] = w
         return w
 
+    def bp_scratch(self, batch: int, device: torch.device) -> Tensor:
+        """Scratch for scd_bp (sample-interleaved copy of the sinograms), cached per device and batch."""
+        h = self._handle(device)
+        key = ('bp', h.device.index, batch)
+        w = self._work.get(key)
+        if w is None:
+            nbytes = int(h._lib.scd_bp_scratch_bytes(h.ptr, batch))
+            w = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+            self._work[key] = w
+        return w
+
     @staticmethod
     def _aligned(w: Tensor):
         p = w.data_ptr()
@@ -226,9 +237,11 @@ class B200RayTrafo(BaseRayTrafo):
             if addend.shape != x.shape:
                 raise ValueError('addend shape %r != %r' % (tuple(addend.shape), tuple(x.shape)))
             add_ptr = addend.data_ptr()
+        scr = self.bp_scratch(batch, y.device)
         with torch.cuda.device(y.device):
             _lib.check(h._lib.scd_bp(h.ptr, y.data_ptr(), x.data_ptr(), batch, lo, hi, float(scale),
-                                     add_ptr, float(addend_scale), _stream_ptr(y.device)), 'scd_bp')
+                                     add_ptr, float(addend_scale), scr.data_ptr(), scr.numel(),
+                                     _stream_ptr(y.device)), 'scd_bp')
         return x
 
     def normal_apply(self, v: Tensor, gamma: float) -> Tensor:

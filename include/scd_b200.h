@@ -80,11 +80,15 @@ int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
 /* A*: out = c_acc * BP(sino; angles [lo,hi)) + c_add * addend
  * where BP is the un-scaled pixel-driven sum; the plain adjoint is
  * c_acc = adj_scale, addend = NULL.
+ * `scratch` is a caller-owned device buffer of at least scd_bp_scratch_bytes(g, batch)
+ * bytes: the sinogram is first re-laid out with the samples interleaved per detector
+ * bin, the form the backprojector's shared-memory segments are bulk-copied from.
  * Replaces: SimpleTrafo.trafo_adjoint -> ODL/ASTRA par_bp
  * (src/physics/trafo.py:61) and the axpy of `op` (src/samplers/utils.py:188-189). */
+size_t scd_bp_scratch_bytes(const scd_geom_t *g, int batch);
 int scd_bp(const scd_geom_t *g, const float *sino, float *out, int batch,
            int angle_lo, int angle_hi, float c_acc, const float *addend,
-           float c_add, void *stream);
+           float c_add, void *scratch, size_t scratch_bytes, void *stream);
 
 /* Bytes of scratch scd_cg / scd_dds_step need for `batch` samples.           */
 size_t scd_cg_workspace_bytes(const scd_geom_t *g, int batch);
@@ -146,7 +150,8 @@ int scd_geom_info(const scd_geom_t *g, int32_t *n0, int32_t *n1,
 int64_t scd_launch_count(void);
 void    scd_launch_count_reset(void);
 /* Override launch heuristics (tuning / tests).  key is one of
- * "fp_samples", "fp_angles", "fp_rows", "fp_threads", "fp_nbuf", "bp_samples", "bp_tile"; value 0
+ * "fp_samples" (samples interleaved per pixel/bin: 1,2,4,8,16), "fp_angles", "fp_rows",
+ * "fp_threads", "fp_nbuf", "fp_cluster", "fp_plan", "bp_tile", "bp_impl", "bp_samples"; value 0
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */
 int scd_set_tuning(scd_geom_t *g, const char *key, int value);
 

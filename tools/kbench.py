@@ -1,4 +1,4 @@
-"""Kernel micro-benchmark / tuning sweep for fp_joseph and bp_pixel (CUDA events, L2 flushed).
+"""Kernel micro-benchmark / tuning sweep for fp_march and bp_tile (CUDA events, L2 flushed).
 
     python tools/kbench.py --kernel fp --batch 8 --sweep
     python tools/kbench.py --kernel fp --batch 256 --set fp_samples=4,fp_angles=2 --iters 5   (for ncu)
@@ -48,7 +48,7 @@ def main():
     nbytes = 4 * (a.im * a.im + rt.obs_shape[0] * rt.obs_shape[1]) * a.batch
 
     def run(tune):
-        keys = ['fp_impl', 'fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'bp_samples', 'bp_tile']
+        keys = ['fp_impl', 'fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'bp_samples', 'bp_tile', 'bp_impl']
         rt.set_tuning(dev, **{k: tune.get(k, 0) for k in keys})
         if a.kernel == 'fp':
             fn = lambda: rt._fp(x)          # noqa: E731
@@ -80,10 +80,11 @@ def main():
                     continue
                 run(dict(fp_samples=SB, fp_angles=NA, fp_rows=TR, fp_cluster=CS, fp_threads=TH, fp_plan=PL))
         elif a.kernel == 'bp':
-            for S, T in itertools.product([1, 2, 4], [16, 32, 64]):
-                if S > a.batch:
+            run(dict(bp_impl=1))
+            for SB, T in itertools.product([4, 8, 16], [16, 32]):
+                if SB > max(4, a.batch):
                     continue
-                run(dict(bp_samples=S, bp_tile=T))
+                run(dict(fp_samples=SB, bp_tile=T))
     else:
         tune = {}
         for kv in a.set.split(','):
