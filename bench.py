@@ -34,9 +34,9 @@ REVERSE_STEPS = 100
 CG_ITER, GAMMA, ETA = 5, 0.01, 0.15
 # algorithmic bytes per sample (fp32), SURVEY.md section 8(d) / BASELINE.md section 4
 BYTES = {
-    'fp_joseph': 4 * (IM * IM + ANGLES * NDET),
-    'bp_pixel': 4 * (IM * IM + ANGLES * NDET),
-    'bp_pixel_axpy_dot': 4 * (2 * IM * IM + ANGLES * NDET),      # + read of the addend
+    'fp_march': 4 * (IM * IM + ANGLES * NDET),
+    'bp_tile': 4 * (IM * IM + ANGLES * NDET),
+    'bp_tile_axpy_dot': 4 * (2 * IM * IM + ANGLES * NDET),      # + read of the addend
     'cg_update_xr': 6 * 4 * IM * IM,
     'cg_update_p': 3 * 4 * IM * IM,
     'tweedie_rhs': 5 * 4 * IM * IM,
@@ -256,9 +256,9 @@ def kernel_sweep(rt, batch, dev, hbm_peak, iters=20):
     tp = torch.ones(batch, device=dev) * 490.
     out = {}
     cases = {
-        'fp_joseph': lambda: rt._fp(x),
-        'bp_pixel': lambda: rt._bp(y, rt.adj_scale),
-        'bp_pixel_axpy_dot': lambda: rt._bp(y, 0.01 * rt.adj_scale, addend=p, addend_scale=1.0),
+        'fp_march': lambda: rt._fp(x),                                     # fp_packq + fp_march launches
+        'bp_tile': lambda: rt._bp(y, rt.adj_scale),                        # sino_pack + bp_tile launches
+        'bp_tile_axpy_dot': lambda: rt._bp(y, 0.01 * rt.adj_scale, addend=p, addend_scale=1.0),
         'tweedie_rhs': lambda: fused.tweedie_rhs(x, s, t, abar, atb=p, gamma=GAMMA),
         'ddim': lambda: fused.ddim_ddpm(x, s, p, t, tp, abar, ETA),
     }
@@ -274,7 +274,7 @@ def kernel_sweep(rt, batch, dev, hbm_peak, iters=20):
     for _ in range(3):
         cg(op, x, p, CG_ITER)
     ms = cuda_time(lambda: cg(op, x, p, CG_ITER), iters, flush)
-    cg_bytes = (CG_ITER + 1) * (BYTES['fp_joseph'] + BYTES['bp_pixel_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
+    cg_bytes = (CG_ITER + 1) * (BYTES['fp_march'] + BYTES['bp_tile_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
         + (CG_ITER - 1) * BYTES['cg_update_p']
     gbs = cg_bytes * batch / (ms * 1e-3) / 1e9
     out['cg_solve_k5'] = {'ms': ms, 'GB/s': gbs, 'frac_hbm': gbs / hbm_peak}
@@ -392,29 +392,32 @@ def run_b200(args):
     dc_only()
     dc_launches = fused.launch_count()
     ms_dc = cuda_time(dc_only, 20)
-    dc_bytes = (CG_ITER + 1) * (BYTES['fp_joseph'] + BYTES['bp_pixel_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
+    dc_bytes = (CG_ITER + 1) * (BYTES['fp_march'] + BYTES['bp_tile_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
         + (CG_ITER - 1) * BYTES['cg_update_p'] + BYTES['tweedie_rhs'] + BYTES['ddim']
 
     line = None
     if rank == 0:
         sweep_small = kernel_sweep(rt, B, dev, hbm_peak)
         sweep_big = kernel_sweep(rt, args.kernel_batch, dev, hbm_peak) if args.kernel_batch else {}
-        dom = max(('fp_joseph', 'bp_pixel_axpy_dot'), key=lambda k: sweep_small[k]['ms'])
+        dom = max(('fp_march', 'bp_tile_axpy_dot'), key=lambda k: sweep_small[k]['ms'])
         traffic, traffic_src = measured_traffic()
-        tr = None
+        tr, pipe = None, None
         if traffic is not None and B == 8:
-            names = ['fp_pack_kernel', 'fp_joseph_kernel'] if dom == 'fp_joseph' else ['bp_pixel_kernel']
+            names = ['fp_packq_kernel', 'fp_march_kernel'] if dom == 'fp_march' else ['sino_pack_kernel', 'bp_tile_kernel']
             if all(n in traffic for n in names):
                 tr = sum(traffic[n]['dram_bytes_per_launch'] for n in names)
-        roofline = {'bound': 'hbm', 'kernel': dom + (' (fp_pack + fp_joseph launches)' if dom == 'fp_joseph' else ''),
+                pipe = traffic[names[-1]].get('shared_pipe_frac')
+        roofline = {'bound': 'hbm', 'kernel': dom + (' (fp_packq + fp_march launches)' if dom == 'fp_march'
+                                                     else ' (sino_pack + bp_tile launches)'),
                     'achieved': sweep_small[dom]['GB/s'], 'peak': hbm_peak,
                     'unit': 'GB/s', 'frac': sweep_small[dom]['frac_hbm'], 'traffic': tr,
                     'traffic_source': traffic_src,
                     'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs, burst copy)' if peak_kind == 'measured'
                     else 'fallback 6.65 TB/s',
                     'algorithmic_bytes_per_launch': BYTES[dom] * B, 'launch_ms': sweep_small[dom]['ms'],
-                    'note': 'A/A* are bound by shared-memory gather bandwidth and issue slots, not HBM '
-                            '(DESIGN.md); large-batch figures in kernels_b%d' % args.kernel_batch}
+                    'shared_memory_pipe_frac_ncu': pipe,
+                    'note': 'A/A* are bound by the shared-memory pipe (8 B per tap pair and sample), not HBM: '
+                            'DESIGN.md section 4; large-batch figures in kernels_b%d' % args.kernel_batch}
         line = {
             'metric': 'SCD samples/sec at 256^2', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,

@@ -55,6 +55,8 @@ sino_pack_kernel(const float *sino, float *sino_il, int n_angles, int n_det, int
                  int angle_lo, int SB, int PADL, int NB, size_t group_floats)
 {
     __shared__ float tile[16][257];
+    scd_pdl_wait();                               // predecessor complete, its writes visible
+    scd_pdl_trigger();
     const int tid = threadIdx.x;
     const int J0 = blockIdx.x * 256, a = angle_lo + blockIdx.y, grp = blockIdx.z;
     const int j = J0 + tid;
@@ -195,6 +197,8 @@ bp_tile_kernel(const BqParams P)
         }
     }
     __syncthreads();
+    scd_pdl_wait();                               // the producer of the sinogram has completed
+    scd_pdl_trigger();
 
     float acc[PPT][V];
 #pragma unroll
@@ -377,7 +381,7 @@ static int bq_launch_t(const BqParams &P, const BqConfig &c, cudaStream_t st)
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
         configured_smem = (int)c.smem;
     }
-    bp_tile_kernel<V, LPR, PPT><<<c.grid, BQ_THREADS, c.smem, st>>>(P);
+    SCD_CUDA(scd_launch_kernel(bp_tile_kernel<V, LPR, PPT>, c.grid, dim3(BQ_THREADS), c.smem, st, 0, P));
     SCD_LAUNCH_CHECK("bp_tile_kernel");
     return 0;
 }
@@ -415,8 +419,8 @@ int scd_launch_sino_pack(const scd_geom *g, const float *sino, float *sino_il, i
     const int groups = (batch + SB - 1) / SB;
     dim3 grid((g->il_nb + 255) / 256, angle_hi - angle_lo, groups);
     if (grid.y > 65535 || grid.z > 65535) { scd_set_error("scd_bp: too many angles / samples"); return SCD_E_INVALID; }
-    sino_pack_kernel<<<grid, 256, 0, st>>>(sino, sino_il, g->n_angles, g->n_det, batch, angle_lo, SB,
-                                           g->il_padl, g->il_nb, (size_t)g->n_angles * g->il_nb * SB);
+    SCD_CUDA(scd_launch_kernel(sino_pack_kernel, grid, dim3(256), 0, st, 0, sino, sino_il, g->n_angles, g->n_det, batch,
+                               angle_lo, SB, g->il_padl, g->il_nb, (size_t)g->n_angles * g->il_nb * SB));
     SCD_LAUNCH_CHECK("sino_pack_kernel");
     return 0;
 }

@@ -63,6 +63,7 @@ struct MqParams {
     int rows_per_cta;        // multiple of 8
     int ring_bytes;          // strip ring (aliased by the partial sums), tables follow
     int il_padl, il_nb;      // interleaved sinogram row: zero bins before / total bins
+    int groups, n_big;       // sample groups; units of the full NA angles (they come first)
     int need_cls[2];
     MqLayout L;
     int n_runs;
@@ -82,6 +83,8 @@ fp_packq_kernel(const MqParams P, const FpPrologue Q)
 {
     __shared__ __align__(16) float tile[PK_T * (PK_T + 1) * 36];
     __shared__ float coef[32][2];
+    scd_pdl_wait();                               // predecessor complete, its writes visible
+    scd_pdl_trigger();
     const int SB = P.L.SB;
     const int SBP = SB >= 4 ? SB + 4 : SB + 1;
     const int grp = blockIdx.z;
@@ -123,24 +126,42 @@ fp_packq_kernel(const MqParams P, const FpPrologue Q)
         const int k0 = K0 + ty, k1 = K1 + tx;
         const bool in_img = k0 < P.n0 && k1 < P.n1;
         float *tp = tile + (ty * (PK_T + 1) + tx) * SBP;
-        for (int s = 0; s < SB; ++s) {
-            const int b = grp * SB + s;
-            float v = 0.f;
-            if (in_img && b < P.batch) {
-                const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
-                if (MODE == 0) {
-                    v = __ldg(P.img + o);
-                } else if (MODE == 1) {
-                    v = fmaf(coef[s][0], Q.p[o], Q.r[o]);
-                    Q.p[o] = v;
-                } else {
-                    const float u = __fsub_rn(Q.x[o], __fmul_rn(Q.s[o], coef[s][0]));
-                    v = __fmul_rn(u, coef[s][1]);
-                    Q.xhat0[o] = v;
-                    Q.b[o] = __fadd_rn(v, __fmul_rn(Q.gamma, Q.atb[o]));
+        // four samples per round: their loads are issued together (memory-level parallelism)
+        for (int s0 = 0; s0 < SB; s0 += 4) {
+            float a[4], c[4], e[4];
+            bool live[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s = s0 + i, b = grp * SB + s;
+                live[i] = in_img && s < SB && b < P.batch;
+                a[i] = c[i] = e[i] = 0.f;
+                if (live[i]) {
+                    const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
+                    if (MODE == 0) a[i] = __ldg(P.img + o);
+                    else if (MODE == 1) { a[i] = Q.p[o]; c[i] = Q.r[o]; }
+                    else { a[i] = Q.x[o]; c[i] = Q.s[o]; e[i] = Q.atb[o]; }
                 }
             }
-            tp[s] = v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int s = s0 + i, b = grp * SB + s;
+                float v = 0.f;
+                if (live[i]) {
+                    const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
+                    if (MODE == 0) {
+                        v = a[i];
+                    } else if (MODE == 1) {
+                        v = fmaf(coef[s][0], a[i], c[i]);
+                        Q.p[o] = v;
+                    } else {
+                        const float u = __fsub_rn(a[i], __fmul_rn(c[i], coef[s][0]));
+                        v = __fmul_rn(u, coef[s][1]);
+                        Q.xhat0[o] = v;
+                        Q.b[o] = __fadd_rn(v, __fmul_rn(Q.gamma, e[i]));
+                    }
+                }
+                if (s < SB) tp[s] = v;
+            }
         }
     }
     __syncthreads();
@@ -283,8 +304,15 @@ fp_march_kernel(const MqParams P)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CS = P.CS;
     const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
-    const int grp = (int)blockIdx.x / CS;
-    const int unit = (int)blockIdx.y;
+    // linear CTA order: first the full-size units, group by group (the units of a group read
+    // the same packed image: L2 locality), then the shorter units, largest first across groups
+    int grp, unit;
+    {
+        const int lin = (int)blockIdx.x / CS;
+        const int nbig_all = P.n_big * P.groups;
+        if (lin < nbig_all) { grp = lin / P.n_big; unit = lin - grp * P.n_big; }
+        else { const int l2 = lin - nbig_all; unit = P.n_big + l2 / P.groups; grp = l2 - (unit - P.n_big) * P.groups; }
+    }
 
     // locate this unit's run without indexing the parameter array dynamically
     MqRun R = P.runs[0];
@@ -334,6 +362,8 @@ fp_march_kernel(const MqParams P)
         if (j == 0) { MqAng a; a.scale = f.scale; a.id = id; ang[ai] = a; }
     }
     __syncthreads();                              // mbarrier init + tables visible
+    scd_pdl_wait();                               // the pack pass has completed: packed image visible
+    scd_pdl_trigger();
 
     float acc[NSLOT][V];
     int eidx[NSLOT];
@@ -610,7 +640,7 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
 // equal chunks of NA angles can leave a third of the machine idle in the last round.  The plan
 // splits each class into chunks of NA angles followed by shorter ones (launched last, largest
 // first: list scheduling) and keeps the split with the smallest simulated makespan.
-struct MqPlan { int n_runs; MqRun runs[MQ_MAX_RUNS]; int units; };
+struct MqPlan { int n_runs; MqRun runs[MQ_MAX_RUNS]; int units, n_big; };
 
 static double mq_makespan(const int *sizes, const int *counts, int nkinds, int jobs_per_unit, int machines)
 {
@@ -683,6 +713,7 @@ static MqPlan mq_plan(const scd_geom *g, const MqConfig &c, int angle_lo, int an
         rest[cl] = cnt[cl] - single[cl] - 2 * pairs[cl];
     }
     for (int cl = 0; cl < 2; ++cl) add(cl, rest[cl], NA);          // includes the remainder chunk (run-local min)
+    pl.n_big = pl.units;
     for (int cl = 0; cl < 2; ++cl) add(cl, 2 * pairs[cl], 2);
     for (int cl = 0; cl < 2; ++cl) add(cl, single[cl], 1);
     return pl;
@@ -708,14 +739,7 @@ static int mq_launch_t(const MqParams &P, dim3 grid, size_t smem, cudaStream_t s
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured_smem = (int)smem;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = dim3(32 * NWT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = P.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    SCD_CUDA(cudaLaunchKernelEx(&cfg, fp_march_kernel<V, LPR, NSLOT, TR, NWT>, P));
+    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P));
     SCD_LAUNCH_CHECK("fp_march_kernel");
     return 0;
 }
@@ -749,18 +773,19 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     {
         if (c.groups > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
         dim3 pg((std::max(g->n1, c.L.rows[1]) + PK_T - 1) / PK_T, (std::max(g->n0, c.L.rows[0]) + PK_T - 1) / PK_T, c.groups);
-        if (Q.mode == 0) fp_packq_kernel<0><<<pg, 256, 0, st>>>(P, Q);
-        else if (Q.mode == 1) fp_packq_kernel<1><<<pg, 256, 0, st>>>(P, Q);
-        else fp_packq_kernel<2><<<pg, 256, 0, st>>>(P, Q);
+        if (Q.mode == 0) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<0>, pg, dim3(256), 0, st, 0, P, Q));
+        else if (Q.mode == 1) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<1>, pg, dim3(256), 0, st, 0, P, Q));
+        else SCD_CUDA(scd_launch_kernel(fp_packq_kernel<2>, pg, dim3(256), 0, st, 0, P, Q));
         SCD_LAUNCH_CHECK("fp_packq_kernel");
     }
 
     const MqPlan pl = mq_plan(g, c, angle_lo, angle_hi);
     if (pl.units == 0) return 0;
-    if (pl.units > 65535) { scd_set_error("scd_fp: too many angle chunks"); return SCD_E_INVALID; }
+    if ((long)pl.units * c.groups * c.CS > 0x7fffffffL) { scd_set_error("scd_fp: too many CTAs"); return SCD_E_INVALID; }
+    P.groups = c.groups; P.n_big = pl.n_big;
     P.n_runs = pl.n_runs;
     for (int i = 0; i < pl.n_runs; ++i) P.runs[i] = pl.runs[i];
-    dim3 grid(gx, pl.units);       // x: (group, cluster rank) -- y: unit, largest first
+    dim3 grid(gx * pl.units);      // linear: see the index decoding at the top of the kernel
     int rc = SCD_E_INVALID;
 #define MQ_CASE(VV, LL, TT)                                                                         \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 16)                                      \

@@ -30,6 +30,12 @@ int scd_cuda_fail(cudaError_t e, const char *what)
 
 void scd_count_launch(int n) { g_launches += n; }
 
+bool scd_pdl_enabled()
+{
+    static const bool on = getenv("SCD_NO_PDL") == nullptr;
+    return on;
+}
+
 extern "C" const char *scd_last_error_string(void) { return g_err; }
 extern "C" const char *scd_version(void) { return "scd_b200 0.1 (sm_100a)"; }
 extern "C" int64_t scd_launch_count(void) { return g_launches; }

@@ -23,6 +23,38 @@ void scd_count_launch(int n = 1);
         scd_count_launch();                                                   \
     } while (0)
 
+// ------------------------------------------------- dependent launches ------
+// Every kernel of the library is launched with programmatic stream serialisation (PDL): it may
+// become resident while its predecessor in the stream drains, runs the part of its prologue that
+// touches no global data produced by earlier kernels (mbarrier init, geometry tables) and then
+// blocks in scd_pdl_wait() until the predecessor has completed and flushed its writes.  All
+// global reads of produced data and ALL global writes come after scd_pdl_wait().
+#ifdef __CUDACC__
+__device__ __forceinline__ void scd_pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void scd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+#endif
+bool scd_pdl_enabled();      // false when the environment variable SCD_NO_PDL is set (A/B runs)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t scd_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                            cudaStream_t st, int cluster_x, Args &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = scd_pdl_enabled() ? 1 : 0;
+    ++n;
+    if (cluster_x > 0) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // -------------------------------------------------------------- geometry ---
 // Forward projector, per angle.  In "tile coordinates" the ray of detector bin
 // j crosses marching row r at interpolation-axis position

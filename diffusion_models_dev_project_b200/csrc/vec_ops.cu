@@ -82,6 +82,8 @@ cg_update_xr_kernel(const float *x_in, float *x, float *__restrict__ r,
                     const float *__restrict__ pd_part, int pd_n, int part_stride,
                     float *__restrict__ rr_new_part, int64_t numel)
 {
+    scd_pdl_wait();                               // predecessor complete, its writes visible
+    scd_pdl_trigger();
     __shared__ float red[VEC_THREADS / 32];
     __shared__ float sc[2];
     const int b = blockIdx.y;
@@ -128,6 +130,8 @@ cg_update_p_kernel(float *__restrict__ p, const float *__restrict__ r,
                    const float *__restrict__ rr_old_part, int rr_old_n,
                    int part_stride, int64_t numel)
 {
+    scd_pdl_wait();                               // predecessor complete, its writes visible
+    scd_pdl_trigger();
     __shared__ float sc[2];
     const int b = blockIdx.y;
     const float rn = sum_partials(rr_new_part + (size_t)b * part_stride, rr_new_n, &sc[0]);
@@ -168,6 +172,8 @@ tweedie_rhs_kernel(const float *__restrict__ x, const float *__restrict__ s,
                    const float *__restrict__ abar, int n_table, float gamma,
                    float *__restrict__ xhat0, float *__restrict__ bvec, int64_t numel)
 {
+    scd_pdl_wait();                               // predecessor complete, its writes visible
+    scd_pdl_trigger();
     const int b = blockIdx.y;
     const float ab = abar_at(abar, n_table, t[b]);
     const float mean = __fsqrt_rn(ab);                       // bar_a.pow(.5)
@@ -217,6 +223,8 @@ ddim_kernel(const float *__restrict__ xhat, const float *__restrict__ s,
             const float *__restrict__ tp, const float *__restrict__ abar, int n_table,
             float eta, float eta2, float *__restrict__ out, int64_t numel)
 {
+    scd_pdl_wait();                               // predecessor complete, its writes visible
+    scd_pdl_trigger();
     const int b = blockIdx.y;
     // mean_t, mean_tminus1 and tbeta in the reference's operation order
     const float m_t = __fsqrt_rn(abar_at(abar, n_table, t[b]));
@@ -273,11 +281,11 @@ int scd_launch_cg_update_xr(const float *x_in, float *x, float *r, const float *
     if (batch <= 0 || numel <= 0) return 0;
     dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, x, r, p, d, x_in))
-        cg_update_xr_kernel<true><<<grid, VEC_THREADS, 0, st>>>(x_in, x, r, p, d, rr_part, rr_n, pd_part, pd_n,
-                                                               part_stride, rr_new_part, numel);
+        SCD_CUDA(scd_launch_kernel(cg_update_xr_kernel<true>, grid, dim3(VEC_THREADS), 0, st, 0, x_in, x, r, p, d, rr_part, rr_n, pd_part, pd_n,
+                                                               part_stride, rr_new_part, numel));
     else
-        cg_update_xr_kernel<false><<<grid, VEC_THREADS, 0, st>>>(x_in, x, r, p, d, rr_part, rr_n, pd_part, pd_n,
-                                                                part_stride, rr_new_part, numel);
+        SCD_CUDA(scd_launch_kernel(cg_update_xr_kernel<false>, grid, dim3(VEC_THREADS), 0, st, 0, x_in, x, r, p, d, rr_part, rr_n, pd_part, pd_n,
+                                                                part_stride, rr_new_part, numel));
     SCD_LAUNCH_CHECK("cg_update_xr_kernel");
     return 0;
 }
@@ -289,11 +297,11 @@ int scd_launch_cg_update_p(float *p, const float *r, const float *rr_new_part, i
     if (batch <= 0 || numel <= 0) return 0;
     dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, p, r))
-        cg_update_p_kernel<true><<<grid, VEC_THREADS, 0, st>>>(p, r, rr_new_part, rr_new_n, rr_old_part,
-                                                              rr_old_n, part_stride, numel);
+        SCD_CUDA(scd_launch_kernel(cg_update_p_kernel<true>, grid, dim3(VEC_THREADS), 0, st, 0, p, r, rr_new_part, rr_new_n, rr_old_part,
+                                                              rr_old_n, part_stride, numel));
     else
-        cg_update_p_kernel<false><<<grid, VEC_THREADS, 0, st>>>(p, r, rr_new_part, rr_new_n, rr_old_part,
-                                                               rr_old_n, part_stride, numel);
+        SCD_CUDA(scd_launch_kernel(cg_update_p_kernel<false>, grid, dim3(VEC_THREADS), 0, st, 0, p, r, rr_new_part, rr_new_n, rr_old_part,
+                                                               rr_old_n, part_stride, numel));
     SCD_LAUNCH_CHECK("cg_update_p_kernel");
     return 0;
 }
@@ -305,9 +313,9 @@ int scd_launch_tweedie_rhs(const float *x, const float *s, const float *atb, con
     if (batch <= 0 || numel <= 0) return 0;
     dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, x, s, atb, xhat0, b))
-        tweedie_rhs_kernel<true><<<grid, VEC_THREADS, 0, st>>>(x, s, atb, t, abar, n_table, gamma, xhat0, b, numel);
+        SCD_CUDA(scd_launch_kernel(tweedie_rhs_kernel<true>, grid, dim3(VEC_THREADS), 0, st, 0, x, s, atb, t, abar, n_table, gamma, xhat0, b, numel));
     else
-        tweedie_rhs_kernel<false><<<grid, VEC_THREADS, 0, st>>>(x, s, atb, t, abar, n_table, gamma, xhat0, b, numel);
+        SCD_CUDA(scd_launch_kernel(tweedie_rhs_kernel<false>, grid, dim3(VEC_THREADS), 0, st, 0, x, s, atb, t, abar, n_table, gamma, xhat0, b, numel));
     SCD_LAUNCH_CHECK("tweedie_rhs_kernel");
     return 0;
 }
@@ -319,9 +327,9 @@ int scd_launch_ddim(const float *xhat, const float *s, const float *eps, const f
     if (batch <= 0 || numel <= 0) return 0;
     dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
     if (vec4_ok(numel, xhat, s, eps, out))
-        ddim_kernel<true><<<grid, VEC_THREADS, 0, st>>>(xhat, s, eps, t, t_prev, abar, n_table, eta, eta2, out, numel);
+        SCD_CUDA(scd_launch_kernel(ddim_kernel<true>, grid, dim3(VEC_THREADS), 0, st, 0, xhat, s, eps, t, t_prev, abar, n_table, eta, eta2, out, numel));
     else
-        ddim_kernel<false><<<grid, VEC_THREADS, 0, st>>>(xhat, s, eps, t, t_prev, abar, n_table, eta, eta2, out, numel);
+        SCD_CUDA(scd_launch_kernel(ddim_kernel<false>, grid, dim3(VEC_THREADS), 0, st, 0, xhat, s, eps, t, t_prev, abar, n_table, eta, eta2, out, numel));
     SCD_LAUNCH_CHECK("ddim_kernel");
     return 0;
 }

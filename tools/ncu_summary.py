@@ -44,5 +44,36 @@ def main(path):
                 print('%-84s %s %s' % (w, r[i], units[i]))
 
 
-if __name__ == '__main__':
+
+
+def table(path):
+    """One line per launch: the figures DESIGN.md quotes (duration, HBM GB/s, L1/L2 hit rates, pipes)."""
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    head, data = rows[0], rows[2:]
+    col = {k: head.index(k) for k in head}
+
+    def g(r, k, default='nan'):
+        return r[col[k]] if k in col else default
+    print('%-34s %9s %7s %5s %8s %8s %7s %7s %7s %7s %7s %7s' % (
+        'kernel', 'us', 'grid', 'regs', 'dram MB', 'HBM GB/s', 'L1hit%', 'L2hit%', 'smem%', 'issue%', 'lts%', 'active%'))
+    for r in data:
+        us = float(g(r, 'gpu__time_duration.sum'))
+        scale = {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}
+        mb = sum(float(g(r, k)) * scale.get(rows[1][col[k]], 1.0) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        wf = float(g(r, 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'))
+        smem = 100.0 * wf / (float(g(r, 'sm__cycles_elapsed.max')) * 148.0)
+        name = g(r, 'Kernel Name').replace('void ', '')[:34]
+        act = 100.0 * float(g(r, 'sm__cycles_active.avg')) / float(g(r, 'sm__cycles_elapsed.max'))
+        print('%-34s %9.1f %7s %5s %8.2f %8.1f %7.1f %7.1f %7.1f %7.1f %7.1f %7.1f' % (
+            name, us, g(r, 'launch__grid_size'), g(r, 'launch__registers_per_thread'), mb, mb / us * 1e3,
+            float(g(r, 'l1tex__t_sector_hit_rate.pct')), float(g(r, 'lts__t_sector_hit_rate.pct')),
+            smem,
+            float(g(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active')),
+            float(g(r, 'lts__throughput.avg.pct_of_peak_sustained_elapsed')), act))
+
+
+if __name__ == '__main__' and len(sys.argv) > 2 and sys.argv[2] == '--table':
+    table(sys.argv[1])
+elif __name__ == '__main__':
     main(sys.argv[1])
