@@ -10,7 +10,7 @@ Public surface (names follow the reference's ``src`` package):
 """
 from .physics import BaseRayTrafo, B200RayTrafo, SimpleTrafo, NormalOp, ParallelBeamGeometry2D, simulate
 from .utils import SDE, VESDE, VPSDE, DDPM, PSNR, cg, _EPSILON_PRED_CLASSES, _SCORE_PRED_CLASSES
-from .samplers import (BaseSampler, tv_loss, _score_model_adpt, apTweedy, ddim,
+from .samplers import (BaseSampler, tv_loss, adaptation_loss, _score_model_adpt, apTweedy, ddim,
                        decomposed_diffusion_sampling_sde_predictor, adapted_ddim_sde_predictor,
                        _adapt, _schedule_jump, wrapper_ddim)
 from .utils.exp_utils import (get_standard_sde, get_standard_ray_trafo, get_standard_sampler,

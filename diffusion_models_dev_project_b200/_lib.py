@@ -36,12 +36,20 @@ SIGNATURES = {
     "scd_bp_scratch_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scd_bp": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_float, _F, C.c_float,
                          C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scd_sino_il_buffer_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "scd_fp_il": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scd_bp_il": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_float, _F, C.c_float, C.c_void_p]),
     "scd_cg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scd_cg": (C.c_int, [C.c_void_p, _F, _F, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_tweedie_rhs": (C.c_int, [_F, _F, _F, _F, _F, C.c_int, C.c_double, _F, _F, C.c_int, C.c_int64, C.c_void_p]),
     "scd_ddim": (C.c_int, [_F, _F, _F, _F, _F, _F, C.c_int, C.c_double, _F, C.c_int, C.c_int64, C.c_void_p]),
     "scd_dds_step": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, _F, C.c_int, C.c_double, C.c_double,
                                C.c_int, _F, _F, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scd_residual_sq_blocks": (C.c_int, [C.c_int64]),
+    "scd_residual_sq": (C.c_int, [_F, _F, _F, _F, C.c_int64, C.c_void_p]),
+    "scd_tv_blocks": (C.c_int, [C.c_int, C.c_int]),
+    "scd_tv_loss": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scd_tv_grad": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scd_fp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "scd_bp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "scd_geom_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

@@ -135,6 +135,34 @@ extern "C" int scd_fp(const scd_geom_t *g, const float *img, float *sino, int ba
     return scd_launch_fp(g, img, sino, nullptr, batch, angle_lo, angle_hi, scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
+// ---- operators on the sample-interleaved sinogram (the form A*A is composed in) ----
+extern "C" size_t scd_sino_il_buffer_bytes(const scd_geom_t *g, int batch)
+{
+    return scd_sino_il_bytes(g, batch);
+}
+
+extern "C" int scd_fp_il(const scd_geom_t *g, const float *img, float *sino_il, int batch,
+                         int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, void *stream)
+{
+    if (((uintptr_t)sino_il & 127) != 0) { scd_set_error("scd_fp_il: sino_il must be 128-byte aligned"); return SCD_E_INVALID; }
+    return scd_launch_fp(g, img, nullptr, sino_il, batch, angle_lo, angle_hi, scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int scd_bp_il(const scd_geom_t *g, const float *sino_il, float *out, int batch,
+                         int angle_lo, int angle_hi, float c_acc, const float *addend, float c_add,
+                         void *stream)
+{
+    if (!g || !sino_il || !out) { scd_set_error("scd_bp_il: null argument"); return SCD_E_INVALID; }
+    if (((uintptr_t)sino_il & 127) != 0) { scd_set_error("scd_bp_il: sino_il must be 128-byte aligned"); return SCD_E_INVALID; }
+    if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
+        scd_set_error("scd_bp_il: bad batch/angle range"); return SCD_E_INVALID;
+    }
+    BpEpilogue e;
+    e.c_acc = c_acc; e.add1 = addend; e.c1 = c_add; e.add2 = nullptr; e.c2 = 0.f;
+    e.out2 = nullptr; e.dot_part = nullptr; e.dot_stride = 0; e.dot_with_add1 = 0;
+    return scd_launch_bp_il(g, sino_il, out, batch, angle_lo, angle_hi, e, (cudaStream_t)stream);
+}
+
 extern "C" size_t scd_bp_scratch_bytes(const scd_geom_t *g, int batch)
 {
     return scd_sino_il_bytes(g, batch);

@@ -770,7 +770,8 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     const unsigned gx = (unsigned)c.groups * c.CS;
 
     // ---- pack: image -> tile-ready layout (both orientations), producer fused in ----
-    {
+    // (fp_skip_pack: benchmarking aid -- march again over the packed copy of the previous call)
+    if (!(g->tune_fp_skip_pack && Q.mode == 0)) {
         if (c.groups > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
         dim3 pg((std::max(g->n1, c.L.rows[1]) + PK_T - 1) / PK_T, (std::max(g->n0, c.L.rows[0]) + PK_T - 1) / PK_T, c.groups);
         if (Q.mode == 0) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<0>, pg, dim3(256), 0, st, 0, P, Q));

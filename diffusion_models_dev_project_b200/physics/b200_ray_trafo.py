@@ -244,10 +244,49 @@ class B200RayTrafo(BaseRayTrafo):
                                      _stream_ptr(y.device)), 'scd_bp')
         return x
 
-    def normal_apply(self, v: Tensor, gamma: float) -> Tensor:
-        """``v + gamma*A*(A v)`` with the axpy fused into the backprojector (no grad)."""
-        q = self._fp(v)
-        return self._bp(q, gamma * self.adj_scale, addend=v, addend_scale=1.0)
+    def _fp_il(self, x: Tensor, angle_range=None) -> Tensor:
+        """A x in the library's sample-interleaved sinogram layout (opaque byte buffer, cached per
+        device and batch: valid until the next ``_fp_il`` of the same batch size)."""
+        x = self._prep(x, self.im_shape, 'trafo')
+        h = self._handle(x.device)
+        batch = int(np.prod(x.shape[:-2])) if x.dim() > 2 else 1
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        key = ('il', h.device.index, batch)
+        buf = self._work.get(key)
+        if buf is None:
+            buf = torch.empty(int(h._lib.scd_sino_il_buffer_bytes(h.ptr, batch)) + 256, dtype=torch.uint8, device=h.device)
+            self._work[key] = buf
+        bp, _ = self._aligned(buf)
+        scr = self.fp_scratch(batch, x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(h._lib.scd_fp_il(h.ptr, x.data_ptr(), bp, batch, lo, hi, scr.data_ptr(), scr.numel(),
+                                        _stream_ptr(x.device)), 'scd_fp_il')
+        return buf
+
+    def _bp_il(self, buf: Tensor, lead, scale: float, addend: Tensor = None, addend_scale: float = 0.0,
+               angle_range=None) -> Tensor:
+        """Backprojection of a buffer written by :meth:`_fp_il` for the same leading shape."""
+        h = self._handle(buf.device)
+        batch = int(np.prod(lead)) if len(lead) else 1
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        x = torch.empty(*lead, *self.im_shape, dtype=torch.float32, device=buf.device)
+        add_ptr = None
+        if addend is not None:
+            addend = self._prep(addend, self.im_shape, 'addend')
+            add_ptr = addend.data_ptr()
+        bp, _ = self._aligned(buf)
+        with torch.cuda.device(buf.device):
+            _lib.check(h._lib.scd_bp_il(h.ptr, bp, x.data_ptr(), batch, lo, hi, float(scale), add_ptr,
+                                        float(addend_scale), _stream_ptr(buf.device)), 'scd_bp_il')
+        return x
+
+    def normal_apply(self, v: Tensor, gamma: float, angle_range=None, add_identity: bool = True) -> Tensor:
+        """``v + gamma*A*(A v)``: the projector writes the sinogram in the layout the backprojector
+        stages from, the axpy is fused into the backprojector's epilogue (no grad)."""
+        v = self._prep(v, self.im_shape, 'normal_apply')
+        q = self._fp_il(v, angle_range)
+        return self._bp_il(q, v.shape[:-2], gamma * self.adj_scale, addend=v if add_identity else None,
+                           addend_scale=1.0 if add_identity else 0.0, angle_range=angle_range)
 
     # --------------------------------------------------- reference interface --
     def trafo(self, x: Tensor) -> Tensor:

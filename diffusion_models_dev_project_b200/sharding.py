@@ -117,7 +117,11 @@ class AngleShardedRayTrafo:
         vf = v.reshape(-1, 1, *self.im_shape)
         out = torch.empty_like(vf)
 
+        fused = getattr(self.base, 'normal_apply', None)      # B200RayTrafo: A*A without re-laying-out the sinogram
+
         def produce(lo, hi):
+            if fused is not None:
+                return fused(vf[lo:hi], gamma, angle_range=self.angle_range, add_identity=False)
             q = self.base._fp(vf[lo:hi], angle_range=self.angle_range)
             return self.base._bp(q, gamma * self.base.adj_scale, angle_range=self.angle_range)
         self._reduce_chunks(produce, vf.shape[0], out)

@@ -90,6 +90,20 @@ int scd_bp(const scd_geom_t *g, const float *sino, float *out, int batch,
            int angle_lo, int angle_hi, float c_acc, const float *addend,
            float c_add, void *scratch, size_t scratch_bytes, void *stream);
 
+/* The same operators on the sample-interleaved sinogram ("sino_il": [group][angle][bins +
+ * zero pads][samples of the group], scd_sino_il_buffer_bytes(g, batch) bytes, 128-byte aligned),
+ * the form in which A*(A x) is composed without re-laying-out the sinogram in between:
+ * scd_fp_il writes it, scd_bp_il reads it.  The layout is internal to the library (it depends on
+ * the batch size); a buffer written for one batch size must be read with the same one.
+ * Replaces: the `ray_trafo.trafo_adjoint(ray_trafo(x))` pairs of `op`
+ * (src/samplers/utils.py:188-189, 235-236, 302-303).                                      */
+size_t scd_sino_il_buffer_bytes(const scd_geom_t *g, int batch);
+int scd_fp_il(const scd_geom_t *g, const float *img, float *sino_il, int batch,
+              int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, void *stream);
+int scd_bp_il(const scd_geom_t *g, const float *sino_il, float *out, int batch,
+              int angle_lo, int angle_hi, float c_acc, const float *addend, float c_add,
+              void *stream);
+
 /* Bytes of scratch scd_cg / scd_dds_step need for `batch` samples.           */
 size_t scd_cg_workspace_bytes(const scd_geom_t *g, int batch);
 
@@ -134,6 +148,18 @@ int scd_dds_step(const scd_geom_t *g, const float *x, const float *s,
                  double gamma, double eta, int n_iter, float *x_next,
                  float *xhat0, int batch, void *work, size_t work_bytes,
                  void *stream);
+
+/* Adaptation loss of SCD, loss(x) = mean((A x - y)^2) + lambda*tv_loss(x)
+ * (src/utils/exp_utils.py:256-257, src/samplers/adaptation.py:7-11):
+ *   scd_residual_sq : r = ax - y, part[k] = block-k partial sum of r^2 (scd_residual_sq_blocks entries)
+ *   scd_tv_loss     : part[image*scd_tv_blocks + k] = partial sums of the cropped |dh| + |dw|
+ *   scd_tv_grad     : grad = d tv_loss / d x
+ * The caller adds the partials (in index order: deterministic).                */
+int scd_residual_sq_blocks(int64_t numel);
+int scd_residual_sq(const float *ax, const float *y, float *r, float *part, int64_t numel, void *stream);
+int scd_tv_blocks(int n0, int n1);
+int scd_tv_loss(const float *x, float *part, int images, int n0, int n1, void *stream);
+int scd_tv_grad(const float *x, float *grad, int images, int n0, int n1, void *stream);
 
 /* Host-buffer variants (pageable or pinned host memory): copy in, run, copy
  * out, synchronise the stream.  These are what a non-PyTorch caller binds.   */

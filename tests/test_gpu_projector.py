@@ -134,6 +134,20 @@ def test_angle_ranges_partition():
     assert rel_l2(acc_x.cpu().numpy(), full_x.cpu().numpy()) < 1e-6
 
 
+def test_normal_apply_composes_without_relayout():
+    """v + gamma A*(A v) through the interleaved sinogram == the two public operators in sequence."""
+    rt = _rt((96, 80), 18)
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    for batch in (1, 3, 8, 21):
+        v = torch.rand(batch, 1, 96, 80, device='cuda', generator=gen)
+        ref = v + 0.05 * rt.trafo_adjoint(rt(v))
+        out = rt.normal_apply(v, 0.05)
+        assert float((out - ref).norm() / ref.norm()) < 1e-6
+        part = rt.normal_apply(v, 0.05, angle_range=(4, 11), add_identity=False)
+        refp = 0.05 * rt._bp(rt._fp(v, angle_range=(4, 11)), rt.adj_scale, angle_range=(4, 11))
+        assert float((part - refp).norm() / refp.norm()) < 1e-6
+
+
 def test_linearity_and_dot_product_full_size():
     """Size-independent properties at the bench size (batch 8): linearity, and <Ax,y> vs <x,A*y>."""
     rt = _rt((256, 256), 60)
