@@ -63,7 +63,7 @@ struct MqParams {
     int rows_per_cta;        // multiple of 8
     int ring_bytes;          // strip ring (aliased by the partial sums), tables follow
     int il_padl, il_nb;      // interleaved sinogram row: zero bins before / total bins
-    int groups, n_big;       // sample groups; units of the full NA angles (they come first)
+    int groups, n_big, n_units;  // sample groups; units of the full NA angles (they come first); all units
     int need_cls[2];
     MqLayout L;
     int n_runs;
@@ -304,14 +304,15 @@ fp_march_kernel(const MqParams P)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CS = P.CS;
     const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
-    // linear CTA order: first the full-size units, group by group (the units of a group read
-    // the same packed image: L2 locality), then the shorter units, largest first across groups
+    // linear CTA order: first the full-size units, then the shorter ones (they fill the last
+    // round of the machine); both group by group -- the units of a group read the same packed
+    // image, so co-resident CTAs share it in L2
     int grp, unit;
     {
         const int lin = (int)blockIdx.x / CS;
         const int nbig_all = P.n_big * P.groups;
         if (lin < nbig_all) { grp = lin / P.n_big; unit = lin - grp * P.n_big; }
-        else { const int l2 = lin - nbig_all; unit = P.n_big + l2 / P.groups; grp = l2 - (unit - P.n_big) * P.groups; }
+        else { const int l2 = lin - nbig_all, nsm = P.n_units - P.n_big; grp = l2 / nsm; unit = P.n_big + (l2 - grp * nsm); }
     }
 
     // locate this unit's run without indexing the parameter array dynamically
@@ -783,7 +784,7 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     const MqPlan pl = mq_plan(g, c, angle_lo, angle_hi);
     if (pl.units == 0) return 0;
     if ((long)pl.units * c.groups * c.CS > 0x7fffffffL) { scd_set_error("scd_fp: too many CTAs"); return SCD_E_INVALID; }
-    P.groups = c.groups; P.n_big = pl.n_big;
+    P.groups = c.groups; P.n_big = pl.n_big; P.n_units = pl.units;
     P.n_runs = pl.n_runs;
     for (int i = 0; i < pl.n_runs; ++i) P.runs[i] = pl.runs[i];
     dim3 grid(gx * pl.units);      // linear: see the index decoding at the top of the kernel
