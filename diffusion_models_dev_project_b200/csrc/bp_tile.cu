@@ -331,13 +331,13 @@ static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_
     c.V = c.SB >= 4 ? 4 : c.SB;
     c.LPR = c.SB / c.V;
     const int WY = BQ_NW / c.LPR;
-    // tile height 16 or 32 rows: 16 unless that makes more than ~16 CTAs per SM
+    // tile height: 8 rows when several lanes share a pixel (measured fastest at B = 8 .. 256: more,
+    // shorter CTAs hide the staging latency), 16 rows for one lane per pixel
     const int groups = (batch + c.SB - 1) / c.SB;
-    int th = 16;
-    const long tiles16 = (long)((g->n1 + 31) / 32) * ((g->n0 + 15) / 16) * groups;
-    if (tiles16 > 16L * g->sm_count) th = 32;
-    if (g->tune_bp_tile == 16 || g->tune_bp_tile == 32) th = g->tune_bp_tile;
-    if (c.LPR == 4) th = 16;                   // 8 pixels x 4 samples per thread would not fit two CTAs per SM
+    int th = c.LPR >= 2 ? 8 : 16;
+    if (g->tune_bp_tile == 8 || g->tune_bp_tile == 16 || g->tune_bp_tile == 32) th = g->tune_bp_tile;
+    if (c.LPR == 4 && th == 32) th = 16;       // 8 pixels x 4 samples per thread would not fit two CTAs per SM
+    if (c.LPR == 1 && th == 8) th = 16;        // 16 warps along k0: at least one pixel each
     c.PPT = th / WY; c.TH = th;
     double span = 0.0;
     for (int i = angle_lo; i < angle_hi; ++i)
@@ -405,7 +405,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     (void)WY;
 #define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st);
     BQ_CASE(1, 1, 1) BQ_CASE(1, 1, 2) BQ_CASE(2, 1, 1) BQ_CASE(2, 1, 2) BQ_CASE(4, 1, 1) BQ_CASE(4, 1, 2)
-    BQ_CASE(4, 2, 2) BQ_CASE(4, 2, 4) BQ_CASE(4, 4, 4)
+    BQ_CASE(4, 2, 1) BQ_CASE(4, 2, 2) BQ_CASE(4, 2, 4) BQ_CASE(4, 4, 2) BQ_CASE(4, 4, 4)
 #undef BQ_CASE
     scd_set_error("scd_bp: unsupported config V=%d LPR=%d PPT=%d", c.V, c.LPR, c.PPT);
     return SCD_E_INVALID;
@@ -460,6 +460,6 @@ int scd_bp_ctas_per_sample_max(const scd_geom *g, int batch)
 {
     // workspace sizing: independent of the tuning knobs
     int n = scd_bp_ctas_per_sample_v1(g, batch);
-    n = std::max(n, ((g->n1 + 31) / 32) * ((g->n0 + 15) / 16));
+    n = std::max(n, ((g->n1 + 31) / 32) * ((g->n0 + 7) / 8));
     return n;
 }

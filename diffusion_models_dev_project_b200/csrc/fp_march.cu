@@ -304,15 +304,16 @@ fp_march_kernel(const MqParams P)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int CS = P.CS;
     const int rank = CS > 1 ? (int)cluster.block_rank() : 0;
-    // linear CTA order: first the full-size units, then the shorter ones (they fill the last
-    // round of the machine); both group by group -- the units of a group read the same packed
-    // image, so co-resident CTAs share it in L2
+    // linear CTA order: first the full-size units, group by group (the units of a group read
+    // the same packed image: co-resident CTAs share it in L2), then the shorter units, largest
+    // first across groups (they level the last round of the machine; measured: ordering them
+    // by group instead costs 7 % at B = 256)
     int grp, unit;
     {
         const int lin = (int)blockIdx.x / CS;
         const int nbig_all = P.n_big * P.groups;
         if (lin < nbig_all) { grp = lin / P.n_big; unit = lin - grp * P.n_big; }
-        else { const int l2 = lin - nbig_all, nsm = P.n_units - P.n_big; grp = l2 / nsm; unit = P.n_big + (l2 - grp * nsm); }
+        else { const int l2 = lin - nbig_all; unit = P.n_big + l2 / P.groups; grp = l2 - (unit - P.n_big) * P.groups; }
     }
 
     // locate this unit's run without indexing the parameter array dynamically
@@ -548,6 +549,7 @@ static bool mq_have_tr(int V, int LPR, int TR)
 static int mq_nslot(int nwt, int need)
 {
     if (nwt == 16) return need <= 6 ? 6 : (need <= 13 ? 13 : 0);
+    if (nwt == 24) return need <= 4 ? 4 : (need <= 8 ? 8 : 0);          // 80 registers per thread
     return need <= 3 ? 3 : (need <= 6 ? 6 : 0);
 }
 
@@ -581,7 +583,19 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
     const int RPW = 32 / c.LPR;
     const int nchunk = (g->n_det + RPW - 1) / RPW;
 
-    c.NWT = (g->tune_fp_threads == 1024 && c.V == 4) ? 32 : 16;
+    // warps per CTA: 15, 23 or 31 marching warps + the producer.  The chunks of a CTA are dealt
+    // round-robin to the marching warps, so the count that divides them most evenly wins (365 bins
+    // = 46 chunks of 8 rays = 2 x 23; 711 bins = 89 chunks ~ 4 x 23): 23 unless told otherwise
+    c.NWT = 16;
+    if (c.V == 4 && c.LPR >= 2) {
+        // few CTAs (at most one per SM even with the row split): latency-bound, more warps help
+        // (B = 32: 72 -> 67 us); many CTAs: the 15-warp shape with more registers wins (B = 256)
+        const int units4 = c.groups * ((n_cls_max + 3) / 4) * 2;
+        if (units4 * 4 <= 2 * g->sm_count) c.NWT = 24;
+    }
+    if (g->tune_fp_threads == 1024 && c.V == 4) c.NWT = 32;
+    else if (g->tune_fp_threads == 768 && c.V == 4) c.NWT = 24;
+    else if (g->tune_fp_threads == 512) c.NWT = 16;
     const int NW = c.NWT - 1;
     // angles per CTA and cluster row split.  Sharing a strip between NA angles divides the
     // L2 -> SM traffic by NA, but the machine wants >= ~3/4 * SMs CTAs: take the largest NA for
@@ -793,13 +807,19 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 16)                                      \
         rc = c.NSLOT == 6 ? mq_launch_t<VV, LL, 6, TT, 16>(P, grid, c.smem, st)                     \
                           : mq_launch_t<VV, LL, 13, TT, 16>(P, grid, c.smem, st);
+#define MQ_CASE24(VV, LL, TT)                                                                       \
+    if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 24)                                      \
+        rc = c.NSLOT == 4 ? mq_launch_t<VV, LL, 4, TT, 24>(P, grid, c.smem, st)                     \
+                          : mq_launch_t<VV, LL, 8, TT, 24>(P, grid, c.smem, st);
 #define MQ_CASE32(VV, LL, TT)                                                                       \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 32)                                      \
         rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, grid, c.smem, st)                     \
                           : mq_launch_t<VV, LL, 6, TT, 32>(P, grid, c.smem, st);
     MQ_CASE(1, 1, 8) MQ_CASE(2, 1, 8) MQ_CASE(4, 1, 8) MQ_CASE(4, 1, 4)
     MQ_CASE(4, 2, 8) MQ_CASE(4, 2, 4) MQ_CASE(4, 4, 4) MQ_CASE(4, 4, 2)
+    MQ_CASE24(4, 1, 8) MQ_CASE24(4, 1, 4) MQ_CASE24(4, 2, 8) MQ_CASE24(4, 2, 4) MQ_CASE24(4, 4, 4) MQ_CASE24(4, 4, 2)
     MQ_CASE32(4, 2, 8) MQ_CASE32(4, 2, 4) MQ_CASE32(4, 4, 4) MQ_CASE32(4, 4, 2)
+#undef MQ_CASE24
 #undef MQ_CASE
 #undef MQ_CASE32
     if (rc == SCD_E_INVALID) scd_set_error("scd_fp: no kernel for V=%d LPR=%d TR=%d warps=%d", c.V, c.LPR, c.TR, c.NWT);

@@ -78,7 +78,8 @@ def test_fp_bp_other_shapes(im_shape, num_angles):
                                   dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_cluster=1), dict(fp_samples=16, fp_angles=3, fp_rows=2, fp_cluster=2),
                                   dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_threads=1024), dict(fp_samples=8, fp_angles=2, fp_rows=8, fp_threads=1024, fp_plan=1),
                                   dict(fp_samples=1, bp_tile=32), dict(fp_samples=2, bp_tile=16), dict(fp_samples=4, bp_tile=32),
-                                  dict(fp_samples=8, bp_tile=32), dict(fp_samples=8, bp_tile=16), dict(fp_samples=16),
+                                  dict(fp_samples=8, bp_tile=32), dict(fp_samples=8, bp_tile=16), dict(fp_samples=8, bp_tile=8), dict(fp_samples=16, bp_tile=8), dict(fp_samples=16),
+                                  dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_threads=768), dict(fp_samples=8, fp_angles=3, fp_rows=8, fp_threads=768, fp_cluster=2), dict(fp_samples=4, fp_threads=768),
                                   dict(bp_impl=1, bp_samples=2, bp_tile=16), dict(bp_impl=1, bp_samples=4, bp_tile=64),
                                   dict(bp_impl=1, bp_samples=1, bp_tile=32)])
 def test_tuning_variants_agree(tune):

@@ -65,26 +65,28 @@ def main():
 
     if a.sweep:
         if a.kernel == 'fp':
-            run(dict(fp_impl=3))
             run(dict())
-            sbs = [sb for sb in (4, 8, 16, 32) if sb <= max(4, a.batch)]
+            sbs = [sb for sb in (4, 8, 16) if sb <= max(4, a.batch)]
             big = a.batch >= 64
-            for SB, NA, TR, CS, TH, PL in itertools.product(sbs, [2, 3, 4], [2, 4, 8], [1, 2, 4, 8], [512, 1024], [0, 1]):
-                if (SB >= 16 and TR == 8) or (SB == 32 and TR != 2) or (SB <= 8 and TR == 2) or (SB == 4 and TH == 1024):
+            for SB, NA, TR, CS, TH in itertools.product(sbs, [2, 4], [2, 4, 8], [1, 2, 4], [512, 768, 1024]):
+                if (SB >= 16 and TR == 8) or (SB <= 8 and TR == 2) or (SB == 4 and TH == 1024):
                     continue
                 if big and (CS > 1 or SB == 4):
                     continue
-                if not big and PL == 1:
-                    continue
                 if CS > 1 and a.batch // SB * (a.angles // NA) * CS > 1200:
                     continue
-                run(dict(fp_samples=SB, fp_angles=NA, fp_rows=TR, fp_cluster=CS, fp_threads=TH, fp_plan=PL))
+                run(dict(fp_samples=SB, fp_angles=NA, fp_rows=TR, fp_cluster=CS, fp_threads=TH))
         elif a.kernel == 'bp':
             run(dict(bp_impl=1))
-            for SB, T in itertools.product([4, 8, 16], [16, 32]):
+            run(dict())
+            for SB, T in itertools.product([4, 8, 16], [8, 16, 32]):
                 if SB > max(4, a.batch):
                     continue
                 run(dict(fp_samples=SB, bp_tile=T))
+        else:
+            run(dict())
+            for TH, PL in itertools.product([512, 768, 1024], [0, 1]):
+                run(dict(fp_threads=TH, fp_plan=PL))
     else:
         tune = {}
         for kv in a.set.split(','):
