@@ -211,6 +211,23 @@ bp_tile_kernel(const BqParams P)
     const int k1 = K1 + wx * RPW + lr;
     const int k0b = K0 + wy * PPT;
 
+    // The epilogue's addends are fetched before the march so that their latency hides behind it
+    // (when they fit in a few registers; taller tiles load them in the epilogue).
+    constexpr bool PREF = PPT * V <= 8;
+    float pa1[PREF ? PPT : 1][V], pa2[PREF ? PPT : 1][V];
+    if (PREF && warp < BQ_NW) {
+#pragma unroll
+        for (int m = 0; m < PPT; ++m)
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = b0 + lq * V + v, k0 = k0b + m;
+                const bool live = b < P.batch && k0 < P.n0 && k1 < P.n1;
+                const size_t o = live ? ((size_t)b * P.n0 + k0) * P.n1 + k1 : 0;
+                pa1[PREF ? m : 0][v] = (live && P.ep.add1) ? P.ep.add1[o] : 0.f;
+                pa2[PREF ? m : 0][v] = (live && P.ep.add2) ? P.ep.add2[o] : 0.f;
+            }
+    }
+
     if (warp == BQ_NW) {
         // ------------------------------ producer warp ------------------------------
         const float *src0 = P.sino_il + (size_t)grp * P.group_floats;
@@ -289,8 +306,8 @@ bp_tile_kernel(const BqParams P)
                     const size_t o = ((size_t)b * P.n0 + k0) * P.n1 + k1;
                     float val = E.c_acc * acc[m][v];
                     float a1 = 0.f;
-                    if (E.add1) { a1 = E.add1[o]; val = fmaf(E.c1, a1, val); }
-                    if (E.add2) val = fmaf(E.c2, E.add2[o], val);
+                    if (E.add1) { a1 = PREF ? pa1[PREF ? m : 0][v] : E.add1[o]; val = fmaf(E.c1, a1, val); }
+                    if (E.add2) val = fmaf(E.c2, PREF ? pa2[PREF ? m : 0][v] : E.add2[o], val);
                     P.out[o] = val;
                     if (E.out2) E.out2[o] = val;
                     dsum[v] += val * (E.dot_with_add1 ? a1 : val);
