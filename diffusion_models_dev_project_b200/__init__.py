@@ -12,7 +12,8 @@ from .physics import BaseRayTrafo, B200RayTrafo, SimpleTrafo, NormalOp, Parallel
 from .utils import SDE, VESDE, VPSDE, DDPM, PSNR, cg, _EPSILON_PRED_CLASSES, _SCORE_PRED_CLASSES
 from .samplers import (BaseSampler, tv_loss, adaptation_loss, _score_model_adpt, apTweedy, ddim,
                        decomposed_diffusion_sampling_sde_predictor, adapted_ddim_sde_predictor,
-                       _adapt, _schedule_jump, wrapper_ddim)
+                       _adapt, _schedule_jump, wrapper_ddim, Euler_Maruyama_sde_predictor, Ancestral_Sampling,
+                       Langevin_sde_corrector)
 from .utils.exp_utils import (get_standard_sde, get_standard_ray_trafo, get_standard_sampler,
                               get_standard_adapted_sampler, get_data_from_ground_truth)
 

@@ -448,6 +448,7 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
                   int angle_lo, int angle_hi, const BpEpilogue &ep, void *scratch, size_t scratch_bytes,
                   cudaStream_t st)
 {
+    if (g && batch == 0) return 0;                 // empty batch: nothing to do (pointers may be null)
     if (!g || !sino || !out) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
         scd_set_error("scd_bp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",

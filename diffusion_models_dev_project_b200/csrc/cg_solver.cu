@@ -152,6 +152,7 @@ extern "C" int scd_bp_il(const scd_geom_t *g, const float *sino_il, float *out, 
                          int angle_lo, int angle_hi, float c_acc, const float *addend, float c_add,
                          void *stream)
 {
+    if (g && batch == 0) return 0;
     if (!g || !sino_il || !out) { scd_set_error("scd_bp_il: null argument"); return SCD_E_INVALID; }
     if (((uintptr_t)sino_il & 127) != 0) { scd_set_error("scd_bp_il: sino_il must be 128-byte aligned"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {

@@ -831,6 +831,7 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, float *sino_
                   int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
                   const FpPrologue *prologue)
 {
+    if (g && batch == 0) return 0;                 // empty batch: nothing to do (pointers may be null)
     if (!g || (!img && !(prologue && prologue->mode != 0)) || (!sino && !sino_il)) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
         scd_set_error("scd_fp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",

@@ -216,6 +216,98 @@ def wrapper_ddim(score, sde: SDE, x: Tensor, time_step, step_size, datafitscale=
     return x.detach(), xhat0.detach()
 
 
+# ---------------------------------- other guidance predictors ----
+# Same boundary as the DDS path: the data-fit term is a callable on images that the drivers
+# build from the ray transform (``nloglik = lambda x: norm(y - ray_trafo(x))``, reference
+# src/utils/exp_utils.py:131,143,178); its gradient reaches A / A* through the autograd
+# Functions of B200RayTrafo, i.e. the CUDA projector kernels.
+def _datafit_grad(nloglik, at: Tensor, wrt: Tensor):
+    loss = nloglik(at)
+    return loss, torch.autograd.grad(outputs=loss, inputs=wrt)[0]
+
+
+def Euler_Maruyama_sde_predictor(score, sde: SDE, x: Tensor, time_step: Tensor, step_size: float,
+                                 nloglik: Optional[callable] = None, datafitscale: Optional[float] = None,
+                                 penalty: Optional[float] = None, aTweedy: bool = False) -> Tuple[Tensor, Tensor]:
+    """Reverse-SDE Euler-Maruyama step for VE / VP schedules (reference :11-67).
+
+    ``aTweedy=False``: the data-fit gradient at ``x`` is subtracted from the score ("naive"
+    guidance); ``aTweedy=True``: diffusion posterior sampling -- the data fit is evaluated at the
+    Tweedie estimate, differentiated through the score model, scaled by ``1/loss`` and applied
+    after the noise is added."""
+    assert not isinstance(sde, DDPM)
+    guided = nloglik is not None
+    if guided:
+        assert datafitscale is not None and penalty is not None
+    x.requires_grad_()
+    s = score(x, time_step)
+    if not aTweedy:
+        s = s.detach()
+    grad = None
+    if guided:
+        target = apTweedy(s=s, x=x, sde=sde, time_step=time_step) if aTweedy else x
+        loss, grad = _datafit_grad(nloglik, target, x)
+        if aTweedy:
+            datafitscale = loss.pow(-1)
+    drift, diffusion = sde.sde(x, time_step)
+    g2 = diffusion[:, None, None, None].pow(2)
+    s_eff = s - penalty * grad * datafitscale if (guided and not aTweedy) else s
+    x_mean = x - (drift - g2 * s_eff) * step_size
+    x_new = x_mean + torch.sqrt(g2 * step_size) * torch.randn_like(x)
+    if guided and aTweedy:
+        x_new = x_new - penalty * grad * datafitscale
+    return x_new.detach(), x_mean.detach()
+
+
+def Ancestral_Sampling(score, sde: SDE, x: Tensor, time_step: Tuple[Tensor, Tensor], step_size: float,
+                       nloglik: Optional[callable] = None, datafitscale: Optional[float] = None,
+                       penalty: Optional[float] = None) -> Tuple[Tensor, Tensor]:
+    """DDPM ancestral step with a fixed ``sigma_i = sqrt(1 - alpha_i)``; with ``nloglik`` it is DPS in
+    the discrete framework (reference :70-125).  Returns ``(x_next, xhat0)``."""
+    assert isinstance(sde, DDPM)
+    t = time_step[0]
+    guided = nloglik is not None
+    if guided:
+        assert penalty is not None
+    with torch.set_grad_enabled(guided):
+        if guided:
+            x.requires_grad_()
+        s = score(x, t)
+        xhat0 = apTweedy(s=s, x=x, sde=sde, time_step=t)
+        if guided:
+            loss, grad = _datafit_grad(nloglik, xhat0, x)
+            datafitscale = loss.pow(-1)
+        std_t = sde.marginal_prob_std(t=t)[:, None, None, None]
+        alpha_t = sde.alphas[int(t[0].item())]
+        x_mean = 1 / torch.sqrt(alpha_t) * (x - (1 - alpha_t) / std_t * s)
+        noise = torch.sqrt(1 - alpha_t) * torch.randn_like(x)
+        if guided:
+            x_mean = x_mean - penalty * grad * datafitscale
+        x_new = x_mean + noise
+    return x_new.detach(), xhat0.detach()
+
+
+def Langevin_sde_corrector(score, sde: SDE, x: Tensor, time_step: Tensor, nloglik: Optional[callable] = None,
+                           datafitscale: Optional[float] = None, penalty: Optional[float] = None,
+                           corrector_steps: int = 1, snr: float = 0.16) -> Tensor:
+    """Langevin MCMC corrector for VE / VP schedules (reference :128-157)."""
+    assert not isinstance(sde, DDPM)
+    guided = nloglik is not None
+    if guided:
+        assert datafitscale is not None and penalty is not None
+    noise_norm = float(x[0].numel()) ** 0.5
+    for _ in range(corrector_steps):
+        x.requires_grad_()
+        direction = score(x, time_step).detach()
+        if guided:
+            _, grad = _datafit_grad(nloglik, x, x)
+            direction = direction - penalty * grad * datafitscale
+        grad_norm = torch.norm(direction.reshape(direction.shape[0], -1), dim=-1).mean()
+        eps = 2 * (snr * noise_norm / grad_norm) ** 2
+        x = x + eps * direction + torch.sqrt(2 * eps) * torch.randn_like(x)
+    return x.detach()
+
+
 # -------------------------------------------------------------- schedule ----
 def _check_times(times, t_0, num_steps):
     assert times[0] > times[1], (times[0], times[1])

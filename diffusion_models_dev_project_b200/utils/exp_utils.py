@@ -16,7 +16,8 @@ import torch
 from .sde import VESDE, VPSDE, DDPM, _EPSILON_PRED_CLASSES
 from ..physics import B200RayTrafo, simulate
 from ..samplers import (BaseSampler, decomposed_diffusion_sampling_sde_predictor,
-                        adapted_ddim_sde_predictor, tv_loss, adaptation_loss, _adapt, _score_model_adpt)
+                        adapted_ddim_sde_predictor, tv_loss, adaptation_loss, _adapt, _score_model_adpt,
+                        Euler_Maruyama_sde_predictor, Ancestral_Sampling)
 
 
 def get_standard_sde(config):
@@ -50,27 +51,45 @@ def _im_shape_of(ray_trafo):
 
 
 def get_standard_sampler(args, config, score, sde, ray_trafo, observation=None, filtbackproj=None, device=None):
+    """Sampler factory with the reference's signature (src/utils/exp_utils.py:123-223).
+
+    ``dds`` (the data-consistency hot path) for every schedule; ``dps`` = diffusion posterior
+    sampling (Euler-Maruyama for VE/VP, ancestral for DDPM); ``naive`` = score + data-fit gradient
+    (VE/VP only, as in the reference).  The reference passes an undefined ``init_chain_fn`` on the
+    VE/VP branch; here the chain always starts from the prior."""
     method = args.method.lower()
-    if method != 'dds':
-        raise NotImplementedError(
-            "method %r: only 'dds' (the data-consistency hot path) is provided by this package" % method)
     shape = _im_shape_of(ray_trafo)
+    eps_pred = any(isinstance(sde, c) for c in _EPSILON_PRED_CLASSES)
     sample_kwargs = {
         'num_steps': int(args.num_steps),
         'batch_size': config.sampling.batch_size,
         'start_time_step': ceil(float(args.pct_chain_elapsed) * int(args.num_steps)),
         'im_shape': [config.model.in_channels, *shape],
         'eps': config.sampling.eps,
-        'predictor': {'eta': float(args.eta), 'gamma': float(args.gamma),
-                      'use_simplified_eqn': True, 'ray_trafo': ray_trafo},
     }
-    if any(isinstance(sde, c) for c in _EPSILON_PRED_CLASSES):
+
+    def nloglik(x):
+        return torch.linalg.norm(observation - ray_trafo(x))
+
+    if method == 'dds':
+        sample_kwargs['predictor'] = {'eta': float(args.eta), 'gamma': float(args.gamma),
+                                      'use_simplified_eqn': True, 'ray_trafo': ray_trafo}
+        predictor = functools.partial(
+            decomposed_diffusion_sampling_sde_predictor, score=score, sde=sde,
+            rhs=ray_trafo.trafo_adjoint(observation), cg_kwargs={'max_iter': int(args.cg_iter)})
+    elif method == 'dps' and eps_pred:
+        sample_kwargs['predictor'] = {'penalty': float(args.penalty)}
+        sample_kwargs['early_stopping_pct'] = float(args.early_stopping_pct)
+        predictor = functools.partial(Ancestral_Sampling, nloglik=nloglik)
+    elif method in ('dps', 'naive') and not eps_pred:
+        sample_kwargs['predictor'] = {'aTweedy': method == 'dps', 'penalty': float(args.penalty)}
+        predictor = functools.partial(Euler_Maruyama_sde_predictor, nloglik=nloglik)
+    else:
+        raise NotImplementedError(method)
+    if eps_pred:
         sample_kwargs['travel_length'] = config.sampling.travel_length
         sample_kwargs['travel_repeat'] = config.sampling.travel_repeat
         assert sample_kwargs['start_time_step'] == 0
-    predictor = functools.partial(
-        decomposed_diffusion_sampling_sde_predictor, score=score, sde=sde,
-        rhs=ray_trafo.trafo_adjoint(observation), cg_kwargs={'max_iter': int(args.cg_iter)})
     return BaseSampler(score=score, sde=sde, predictor=predictor, sample_kwargs=sample_kwargs,
                        device=device if device is not None else config.device)
 

@@ -147,10 +147,49 @@ def dds_small_fixture():
     np.savez_compressed(os.path.join(OUT, 'dds_small.npz'), gt=gt.numpy(), y=y.numpy(), recon=recon.numpy())
 
 
+def predictors_fixture():
+    """One step of the other guidance predictors (Euler-Maruyama naive / DPS on a VP schedule, ancestral
+    DDPM unconditional / DPS, Langevin corrector), reference code on CPU, oracle operator."""
+    from src.samplers.utils import (Euler_Maruyama_sde_predictor as ref_em, Ancestral_Sampling as ref_anc,
+                                    Langevin_sde_corrector as ref_lang)
+    from src.utils.sde import VPSDE as RefVPSDE
+    geom = O.OracleGeometry((24, 24), 8)
+    rt = O.OracleRayTrafo(geom)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 1, 24, 24, generator=g)
+    gt = torch.rand(2, 1, 24, 24, generator=g)
+    y = rt(gt)
+    nll = lambda v: torch.linalg.norm(y - rt(v))          # noqa: E731
+    score = BlurScore()
+    res = {'x': x.numpy(), 'y': y.numpy()}
+
+    class VpScore(torch.nn.Module):                          # score-matching output for a VP schedule
+        def forward(self, v, t):
+            return -0.7 * v + 0.1 * torch.tanh(v) * t[:, None, None, None]
+    vp, vscore = RefVPSDE(), VpScore()
+    tv = torch.ones(2) * 0.4
+    for name, kw in (('em_plain', {}), ('em_naive', dict(nloglik=nll, datafitscale=0.4, penalty=0.3, aTweedy=False)),
+                     ('em_dps', dict(nloglik=nll, datafitscale=0.4, penalty=0.3, aTweedy=True))):
+        torch.manual_seed(5)
+        a, b = ref_em(score=vscore, sde=vp, x=x.clone(), time_step=tv, step_size=1e-2, **kw)
+        res[name + '_x'], res[name + '_mean'] = a.numpy(), b.numpy()
+    torch.manual_seed(6)
+    res['langevin'] = ref_lang(score=vscore, sde=vp, x=x.clone(), time_step=tv, nloglik=nll, datafitscale=0.4,
+                               penalty=0.3, corrector_steps=2).numpy()
+    sde = RefDDPM()
+    ts = (torch.ones(2) * 400., torch.ones(2) * 390.)
+    for name, kw in (('anc_plain', {}), ('anc_dps', dict(nloglik=nll, penalty=0.5))):
+        torch.manual_seed(7)
+        a, b = ref_anc(score=score, sde=sde, x=x.clone(), time_step=ts, step_size=1, **kw)
+        res[name + '_x'], res[name + '_xhat0'] = a.numpy(), b.numpy()
+    np.savez_compressed(os.path.join(OUT, 'predictors_small.npz'), **res)
+
+
 if __name__ == '__main__':
     schedule_fixture()
     tweedie_ddim_fixture()
     cg_fixture()
     dds_small_fixture()
+    predictors_fixture()
     dds_fixture()
     print('golden vectors written to', OUT)

@@ -94,6 +94,41 @@ def test_tuning_variants_agree(tune):
     assert rel_l2(rt.trafo_adjoint(torch.from_numpy(g).cuda()).cpu().numpy(), O.bp(geom, g)) < TOL
 
 
+@pytest.mark.parametrize('batch', [0, 5, 17, 33])
+def test_ragged_groups_and_empty_batch(batch):
+    """Batches that do not fill the last sample group (and the empty batch): every sample correct."""
+    geom = O.OracleGeometry((80, 64), 11)
+    rt = _rt((80, 64), 11)
+    rng = np.random.default_rng(6)
+    x = rng.random((batch, 1, 80, 64), dtype=np.float32)
+    y = rt(torch.from_numpy(x).cuda())
+    assert y.shape == (batch, 1, *geom.obs_shape)
+    g = rng.standard_normal((batch, 1, *geom.obs_shape)).astype(np.float32)
+    z = rt.trafo_adjoint(torch.from_numpy(g).cuda())
+    assert z.shape == (batch, 1, 80, 64)
+    if batch:
+        idx = sorted({0, batch // 2, batch - 1})
+        assert rel_l2(y.cpu().numpy()[idx], O.fp(geom, x[idx])) < TOL
+        assert rel_l2(z.cpu().numpy()[idx], O.bp(geom, g[idx])) < TOL
+        v = torch.from_numpy(x).cuda()
+        ref = v + 0.03 * rt.trafo_adjoint(rt(v))
+        assert float((rt.normal_apply(v, 0.03) - ref).norm() / ref.norm()) < 1e-6
+
+
+@pytest.mark.parametrize('im_shape,num_angles', [((1024, 1024), 3), ((16, 16), 1), ((700, 40), 4)])
+def test_extreme_shapes(im_shape, num_angles):
+    """Largest supported strips (1024^2: fewer samples per group), a single angle, a very elongated image."""
+    geom = O.OracleGeometry(im_shape, num_angles)
+    rt = _rt(im_shape, num_angles)
+    rng = np.random.default_rng(7)
+    x = rng.random((3, 1, *im_shape), dtype=np.float32)
+    y = rt(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert rel_l2(y, O.fp(geom, x)) < TOL
+    g = rng.standard_normal((3, 1, *geom.obs_shape)).astype(np.float32)
+    z = rt.trafo_adjoint(torch.from_numpy(g).cuda()).cpu().numpy()
+    assert rel_l2(z, O.bp(geom, g)) < TOL
+
+
 def test_known_answers_disc_and_ones():
     """Analytic line integrals: centred disc -> 2*sqrt(R^2-s^2); A*(1) = pi inside the FOV."""
     rt = _rt((256, 256), 60)

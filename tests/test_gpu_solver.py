@@ -229,6 +229,59 @@ def test_adaptation_loss_fused_matches_tensor_expression():
         assert rel_l2(xa.grad.cpu().numpy(), xb.grad.cpu().numpy()) < 1e-5
 
 
+def test_dps_predictors_differentiate_through_the_cuda_projector(golden, monkeypatch):
+    """DPS (ancestral, DDPM) and Euler-Maruyama DPS (VP) on the GPU: the data-fit gradient flows through
+    fp_march / bp_tile via the autograd Functions.  The CPU golden uses the exact transpose of A in the
+    backward, the ODL pairing uses the pixel-driven A*/c_w: agreement to the matched/unmatched gap."""
+    from scorenet import BlurScore
+    pkg = _pkg()
+    d = golden('predictors_small.npz')
+    rt = pkg.B200RayTrafo((24, 24), 8)
+    x = torch.from_numpy(d['x']).cuda()
+    y = torch.from_numpy(d['y']).cuda()
+    nll = lambda v: torch.linalg.norm(y - rt(v))          # noqa: E731
+    torch.manual_seed(7)
+    noise = torch.randn(2, 1, 24, 24)
+    monkeypatch.setattr(torch, 'randn_like', lambda t: noise.to(t.device))
+    sde, score = pkg.DDPM(), BlurScore().cuda()
+    ts = (torch.ones(2, device='cuda') * 400., torch.ones(2, device='cuda') * 390.)
+    a, b = pkg.Ancestral_Sampling(score=score, sde=sde, x=x.clone(), time_step=ts, step_size=1, nloglik=nll, penalty=0.5)
+    assert rel_l2(b.cpu().numpy(), d['anc_dps_xhat0']) < 1e-5
+    assert rel_l2(a.cpu().numpy(), d['anc_dps_x']) < 2e-2
+    a0, _ = pkg.Ancestral_Sampling(score=score, sde=sde, x=x.clone(), time_step=ts, step_size=1)
+    assert rel_l2(a0.cpu().numpy(), d['anc_plain_x']) < 1e-5
+    assert float((a - a0).abs().max()) > 0                    # the guidance term acted
+
+
+def test_dds_step_is_cuda_graph_capturable():
+    """The library never allocates or synchronises: a whole data-consistency step (24 launches with
+    programmatic dependent launch) captures into a CUDA graph and replays with new inputs."""
+    pkg = _pkg()
+    rt = pkg.B200RayTrafo((96, 96), 20)
+    dev = torch.device('cuda')
+    gen = torch.Generator(device=dev).manual_seed(8)
+    B = 4
+    abar = pkg.DDPM().alpha_bar_table(dev)
+    x = torch.rand(B, 1, 96, 96, device=dev, generator=gen)
+    s = torch.randn(B, 1, 96, 96, device=dev, generator=gen)
+    eps = torch.randn(B, 1, 96, 96, device=dev, generator=gen)
+    atb = rt.trafo_adjoint(rt(torch.rand(B, 1, 96, 96, device=dev, generator=gen)))
+    t = torch.ones(B, device=dev) * 700.
+    tp = torch.ones(B, device=dev) * 690.
+    rt.dds_step(x, s, atb, eps, t, tp, abar, 0.05, 0.15, 3)               # warm-up: handles, workspace
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, xh = rt.dds_step(x, s, atb, eps, t, tp, abar, 0.05, 0.15, 3)
+    for k in range(2):
+        x.copy_(torch.rand(B, 1, 96, 96, device=dev, generator=gen))
+        s.copy_(torch.randn(B, 1, 96, 96, device=dev, generator=gen))
+        t.fill_(500. - 100 * k); tp.fill_(490. - 100 * k)
+        graph.replay()
+        ref, refh = rt.dds_step(x, s, atb, eps, t, tp, abar, 0.05, 0.15, 3)
+        assert torch.equal(out, ref) and torch.equal(xh, refh)
+
+
 def test_fbp_inverts_dense_view_projection():
     pkg = _pkg()
     rt = pkg.B200RayTrafo((128, 128), 360)

@@ -202,6 +202,38 @@ def test_sampler_with_generic_operator_matches_reference_chain(golden):
     assert rel_l2(recon.numpy(), d['recon']) < 1e-5
 
 
+def test_other_guidance_predictors_match_reference(golden):
+    """Euler-Maruyama (plain / naive / DPS), Langevin corrector and ancestral sampling (plain / DPS): one
+    step each on CPU with the oracle operator against the reference's own functions (same seeds)."""
+    from scorenet import BlurScore
+    d = golden('predictors_small.npz')
+    rt = O.OracleRayTrafo(O.OracleGeometry((24, 24), 8))
+    x = torch.from_numpy(d['x'])
+    y = torch.from_numpy(d['y'])
+    nll = lambda v: torch.linalg.norm(y - rt(v))          # noqa: E731
+
+    class VpScore(torch.nn.Module):
+        def forward(self, v, t):
+            return -0.7 * v + 0.1 * torch.tanh(v) * t[:, None, None, None]
+    vp, vscore = pkg.VPSDE(), VpScore()
+    tv = torch.ones(2) * 0.4
+    for name, kw in (('em_plain', {}), ('em_naive', dict(nloglik=nll, datafitscale=0.4, penalty=0.3, aTweedy=False)),
+                     ('em_dps', dict(nloglik=nll, datafitscale=0.4, penalty=0.3, aTweedy=True))):
+        torch.manual_seed(5)
+        a, b = pkg.Euler_Maruyama_sde_predictor(score=vscore, sde=vp, x=x.clone(), time_step=tv, step_size=1e-2, **kw)
+        assert rel_l2(a.numpy(), d[name + '_x']) < 1e-6 and rel_l2(b.numpy(), d[name + '_mean']) < 1e-6, name
+    torch.manual_seed(6)
+    out = pkg.Langevin_sde_corrector(score=vscore, sde=vp, x=x.clone(), time_step=tv, nloglik=nll, datafitscale=0.4,
+                                     penalty=0.3, corrector_steps=2)
+    assert rel_l2(out.numpy(), d['langevin']) < 1e-6
+    sde, score = pkg.DDPM(), BlurScore()
+    ts = (torch.ones(2) * 400., torch.ones(2) * 390.)
+    for name, kw in (('anc_plain', {}), ('anc_dps', dict(nloglik=nll, penalty=0.5))):
+        torch.manual_seed(7)
+        a, b = pkg.Ancestral_Sampling(score=score, sde=sde, x=x.clone(), time_step=ts, step_size=1, **kw)
+        assert rel_l2(a.numpy(), d[name + '_x']) < 1e-6 and rel_l2(b.numpy(), d[name + '_xhat0']) < 1e-6, name
+
+
 def test_adapted_predictor_and_adapt_run_with_autograd():
     """SCD step on CPU with a tiny trainable score: _adapt changes the trainable parameters through
     Tweedie -> CG -> loss, and the adapted predictor returns finite tensors of the right shape."""
