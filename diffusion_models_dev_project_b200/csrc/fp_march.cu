@@ -77,16 +77,15 @@ struct MqParams {
 //   mode 1  CG direction update   p = r + beta p        (reference src/utils/cg.py:35-38)
 //   mode 2  Tweedie + CG rhs      xhat0, b              (reference src/samplers/utils.py:370-378, :197)
 #define PK_T 16
-template <int MODE>
+template <int MODE, int SB>
 __global__ void __launch_bounds__(256)
 fp_packq_kernel(const MqParams P, const FpPrologue Q)
 {
-    __shared__ __align__(16) float tile[PK_T * (PK_T + 1) * 36];
-    __shared__ float coef[32][2];
+    constexpr int SBP = SB >= 4 ? SB + 4 : SB + 1;
+    __shared__ __align__(16) float tile[PK_T * (PK_T + 1) * SBP];
+    __shared__ float coef[SB][2];
     scd_pdl_wait();                               // predecessor complete, its writes visible
     scd_pdl_trigger();
-    const int SB = P.L.SB;
-    const int SBP = SB >= 4 ? SB + 4 : SB + 1;
     const int grp = blockIdx.z;
     const int tid = threadIdx.x;
     const int K0 = blockIdx.y * PK_T, K1 = blockIdx.x * PK_T;
@@ -167,8 +166,8 @@ fp_packq_kernel(const MqParams P, const FpPrologue Q)
     __syncthreads();
 
     // ---- write both orientations: lanes = (pixel, quad of samples), 16 B (or 4*V B) per lane ----
-    const int VQ = SB >= 4 ? 4 : SB;              // floats per lane
-    const int LQ = SB / VQ;                       // lanes per pixel
+    constexpr int VQ = SB >= 4 ? 4 : SB;          // floats per lane
+    constexpr int LQ = SB / VQ;                   // lanes per pixel
     float *dst = P.packed + (size_t)grp * P.L.group_floats;
 #pragma unroll 1
     for (int cls = 0; cls < 2; ++cls) {
@@ -789,9 +788,14 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     if (!(g->tune_fp_skip_pack && Q.mode == 0)) {
         if (c.groups > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
         dim3 pg((std::max(g->n1, c.L.rows[1]) + PK_T - 1) / PK_T, (std::max(g->n0, c.L.rows[0]) + PK_T - 1) / PK_T, c.groups);
-        if (Q.mode == 0) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<0>, pg, dim3(256), 0, st, 0, P, Q));
-        else if (Q.mode == 1) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<1>, pg, dim3(256), 0, st, 0, P, Q));
-        else SCD_CUDA(scd_launch_kernel(fp_packq_kernel<2>, pg, dim3(256), 0, st, 0, P, Q));
+#define PK_CASE(SS)                                                                                  \
+        if (c.SB == SS) {                                                                               \
+            if (Q.mode == 0) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<0, SS>, pg, dim3(256), 0, st, 0, P, Q));       \
+            else if (Q.mode == 1) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<1, SS>, pg, dim3(256), 0, st, 0, P, Q));  \
+            else SCD_CUDA(scd_launch_kernel(fp_packq_kernel<2, SS>, pg, dim3(256), 0, st, 0, P, Q));                   \
+        }
+        PK_CASE(1) PK_CASE(2) PK_CASE(4) PK_CASE(8) PK_CASE(16)
+#undef PK_CASE
         SCD_LAUNCH_CHECK("fp_packq_kernel");
     }
 
