@@ -57,6 +57,7 @@ SIGNATURES = {
     "scd_launch_count": (C.c_int64, []),
     "scd_launch_count_reset": (None, []),
     "scd_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "scd_debug_set_stamps": (None, [C.c_void_p]),
     "scd_last_error_string": (C.c_char_p, []),
     "scd_version": (C.c_char_p, []),
 }

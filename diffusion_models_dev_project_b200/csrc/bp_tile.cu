@@ -45,6 +45,7 @@ struct BqParams {
     int PADL, NB;            // interleaved sinogram row
     size_t group_floats;     // n_angles * NB * SB
     BpEpilogue ep;
+    unsigned long long *dbg;     // time stamps (scd_debug_set_stamps) or NULL
 };
 
 // ------------------------------------------------------------ sino pack ---
@@ -178,6 +179,7 @@ bp_tile_kernel(const BqParams P)
     float4 *cst = reinterpret_cast<float4 *>(empty + BQ_MAX_NBUF);
     float *red = reinterpret_cast<float *>(cst + nang);
 
+    scd_stamp(P.dbg, 0);                          // CTA start
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) { bq_mbar_init(&full[i], 1); bq_mbar_init(&empty[i], BQ_NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -197,8 +199,10 @@ bp_tile_kernel(const BqParams P)
         }
     }
     __syncthreads();
+    scd_stamp(P.dbg, 1);                          // tables done
     scd_pdl_wait();                               // the producer of the sinogram has completed
     scd_pdl_trigger();
+    scd_stamp(P.dbg, 2);                          // predecessor complete
 
     float acc[PPT][V];
 #pragma unroll
@@ -258,6 +262,7 @@ bp_tile_kernel(const BqParams P)
         int bi = 0; unsigned ph = 0;
         for (int c = 0; c < nchunks; ++c) {
             bq_mbar_wait(&full[bi], ph);
+            if (c == 0) scd_stamp(P.dbg, 3);      // first angle chunk landed (warp 0)
             const int nac = min(AC, nang - c * AC);
             unsigned seg = lane_base + (unsigned)(bi * AC) * SEGB;
             unsigned ca = cst_base + (unsigned)(c * AC) * 16u;
@@ -290,6 +295,7 @@ bp_tile_kernel(const BqParams P)
     }
 
     // ---- epilogue: axpy, second output, dot-product partials ---------------
+    if (warp == 0 && lane == 0 && P.dbg) scd_stamp(P.dbg, 4);       // warp 0 done marching
     const BpEpilogue &E = P.ep;
     float dsum[V];
 #pragma unroll
@@ -336,6 +342,7 @@ bp_tile_kernel(const BqParams P)
             }
         }
     }
+    scd_stamp(P.dbg, 5);                          // thread 0 done with the epilogue
 }
 
 // ------------------------------------------------------------- host side ---
@@ -417,7 +424,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
     P.angle_lo = angle_lo; P.angle_hi = angle_hi; P.SEG = c.SEG; P.AC = c.AC; P.nbuf = c.nbuf;
     P.PADL = g->il_padl; P.NB = g->il_nb; P.group_floats = (size_t)g->n_angles * g->il_nb * c.SB;
-    P.ep = ep;
+    P.ep = ep; P.dbg = scd_debug_stamps();
     const int WY = BQ_NW / c.LPR;
     (void)WY;
 #define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st);

@@ -63,6 +63,7 @@ struct MqParams {
     int rows_per_cta;        // multiple of 8
     int ring_bytes;          // strip ring (aliased by the partial sums), tables follow
     int il_padl, il_nb;      // interleaved sinogram row: zero bins before / total bins
+    unsigned long long *dbg;     // time stamps (scd_debug_set_stamps) or NULL
     int groups, n_big, n_units;  // sample groups; units of the full NA angles (they come first); all units
     int need_cls[2];
     MqLayout L;
@@ -350,6 +351,7 @@ fp_march_kernel(const MqParams P)
     const float *src = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[cls] +
                        (size_t)r_begin * pitch * SB;
 
+    scd_stamp(P.dbg, 0);                          // CTA start
     if (tid == 0) {
         for (int i = 0; i < NBUF; ++i) { mq_mbar_init(&full[i], 1); mq_mbar_init(&empty[i], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -363,8 +365,10 @@ fp_march_kernel(const MqParams P)
         if (j == 0) { MqAng a; a.scale = f.scale; a.id = id; ang[ai] = a; }
     }
     __syncthreads();                              // mbarrier init + tables visible
+    scd_stamp(P.dbg, 1);                          // tables done
     scd_pdl_wait();                               // the pack pass has completed: packed image visible
     scd_pdl_trigger();
+    scd_stamp(P.dbg, 2);                          // predecessor complete
 
     float acc[NSLOT][V];
     int eidx[NSLOT];
@@ -407,6 +411,7 @@ fp_march_kernel(const MqParams P)
         int bi = 0; unsigned ph = 0;
         for (int st = 0; st < nst; ++st) {
             mq_mbar_wait(&full[bi], ph);
+            if (st == 0) scd_stamp(P.dbg, 3);     // first strip landed (warp 0)
             const unsigned sbuf = lane_base + (unsigned)bi * strip_bytes;
             const float r0f = (float)(r_begin + st * TR);
 #pragma unroll
@@ -446,6 +451,7 @@ fp_march_kernel(const MqParams P)
         }
     }
     __syncthreads();                              // all strips consumed: the ring can be reused
+    scd_stamp(P.dbg, 4);                          // march done
 
     // ---- partial line integrals -> red[s][e] ------------------------------
     if (warp < NW) {
@@ -458,6 +464,7 @@ fp_march_kernel(const MqParams P)
         }
     }
     if (CS > 1) cluster.sync(); else __syncthreads();
+    scd_stamp(P.dbg, 5);                          // partials exchanged
 
     // ---- add the row-split partials in rank order, scale, write (coalesced along the detector) ----
     const int per = (E + CS - 1) / CS;
@@ -505,7 +512,9 @@ fp_march_kernel(const MqParams P)
             }
         }
     }
+    scd_stamp(P.dbg, 6);                          // output written
     if (CS > 1) cluster.sync();                   // keep red alive until every rank has read it
+    scd_stamp(P.dbg, 7);
 }
 
 // ------------------------------------------------------------- host side ---
@@ -802,7 +811,7 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     const MqPlan pl = mq_plan(g, c, angle_lo, angle_hi);
     if (pl.units == 0) return 0;
     if ((long)pl.units * c.groups * c.CS > 0x7fffffffL) { scd_set_error("scd_fp: too many CTAs"); return SCD_E_INVALID; }
-    P.groups = c.groups; P.n_big = pl.n_big; P.n_units = pl.units;
+    P.groups = c.groups; P.n_big = pl.n_big; P.n_units = pl.units; P.dbg = scd_debug_stamps();
     P.n_runs = pl.n_runs;
     for (int i = 0; i < pl.n_runs; ++i) P.runs[i] = pl.runs[i];
     dim3 grid(gx * pl.units);      // linear: see the index decoding at the top of the kernel

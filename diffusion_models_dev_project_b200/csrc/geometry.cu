@@ -30,6 +30,10 @@ int scd_cuda_fail(cudaError_t e, const char *what)
 
 void scd_count_launch(int n) { g_launches += n; }
 
+static unsigned long long *g_stamps = nullptr;
+unsigned long long *scd_debug_stamps() { return g_stamps; }
+extern "C" void scd_debug_set_stamps(void *device_buffer) { g_stamps = (unsigned long long *)device_buffer; }
+
 bool scd_pdl_enabled()
 {
     static const bool on = getenv("SCD_NO_PDL") == nullptr;

@@ -33,7 +33,19 @@ void scd_count_launch(int n = 1);
 __device__ __forceinline__ void scd_pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void scd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 #endif
-bool scd_pdl_enabled();      // false when the environment variable SCD_NO_PDL is set (A/B runs)
+bool scd_pdl_enabled();
+// optional per-CTA time stamps (tools/timeline.py): device buffer of 8 x int64 per CTA, or NULL
+unsigned long long *scd_debug_stamps();
+#ifdef __CUDACC__
+__device__ __forceinline__ void scd_stamp(unsigned long long *dbg, int slot)
+{
+    if (dbg && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + slot] = t;
+    }
+}
+#endif      // false when the environment variable SCD_NO_PDL is set (A/B runs)
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t scd_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,

@@ -181,6 +181,10 @@ void    scd_launch_count_reset(void);
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */
 int scd_set_tuning(scd_geom_t *g, const char *key, int value);
 
+/* Profiling aid (tools/timeline.py): when set to a device buffer of 8 x int64 per CTA, fp_march and
+ * bp_tile record %globaltimer at their phase boundaries.  NULL (default) disables it.     */
+void scd_debug_set_stamps(void *device_buffer);
+
 const char *scd_last_error_string(void);
 const char *scd_version(void);
 
