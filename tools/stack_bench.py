@@ -75,7 +75,10 @@ def main():
         xs = x[:a.check]
         y_full = rt(xs)
         y_loc = sh(xs)
-        errs['A_own_rows_equal'] = bool(torch.equal(y_loc[..., lo:hi, :], y_full[..., lo:hi, :]))
+        # not bit-equal in general: the row split (cluster size) is chosen per launch, and it fixes the
+        # order in which a line integral's partial sums are added
+        errs['A_own_rows_rel_l2'] = float((y_loc[..., lo:hi, :] - y_full[..., lo:hi, :]).norm()
+                                          / y_full[..., lo:hi, :].norm())
         z_full = rt.trafo_adjoint(y_full)
         z_sh = sh.trafo_adjoint(y_full)
         errs['Aadj_rel_l2'] = float((z_sh - z_full).norm() / z_full.norm())
