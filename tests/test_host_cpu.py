@@ -202,6 +202,18 @@ def test_sampler_with_generic_operator_matches_reference_chain(golden):
     assert rel_l2(recon.numpy(), d['recon']) < 1e-5
 
 
+def test_metrics_psnr_ssim():
+    rng = np.random.default_rng(0)
+    gt = rng.random((64, 48))
+    assert pkg.PSNR(gt, gt) == float('inf') and abs(pkg.SSIM(gt, gt) - 1.0) < 1e-12
+    noisy = gt + 0.1 * rng.standard_normal(gt.shape)
+    mse = np.mean((noisy - gt) ** 2)
+    assert abs(pkg.PSNR(noisy, gt) - 10 * np.log10((gt.max() - gt.min()) ** 2 / mse)) < 1e-9
+    s1, s2 = pkg.SSIM(noisy, gt), pkg.SSIM(gt + 0.3 * rng.standard_normal(gt.shape), gt)
+    assert 0 < s2 < s1 < 1                                   # monotone in the noise level
+    assert abs(pkg.SSIM(gt + 0.2, gt, data_range=1.0) - pkg.SSIM(gt, gt + 0.2, data_range=1.0)) < 1e-12   # symmetric
+
+
 def test_other_guidance_predictors_match_reference(golden):
     """Euler-Maruyama (plain / naive / DPS), Langevin corrector and ancestral sampling (plain / DPS): one
     step each on CPU with the oracle operator against the reference's own functions (same seeds)."""
