@@ -453,54 +453,50 @@ fp_march_kernel(const MqParams P)
     __syncthreads();                              // all strips consumed: the ring can be reused
     scd_stamp(P.dbg, 4);                          // march done
 
-    // ---- partial line integrals -> red[s][e] ------------------------------
+    // ---- partial line integrals -> red[e][SB] (the V samples of a lane: one vector store) ----
     if (warp < NW) {
 #pragma unroll
         for (int k = 0; k < NSLOT; ++k) {
             if ((livemask >> k) & 1u) {
+                VT pv;
+                float *pf = reinterpret_cast<float *>(&pv);
 #pragma unroll
-                for (int v = 0; v < V; ++v) red[(size_t)(lq * V + v) * E + eidx[k]] = acc[k][v];
+                for (int v = 0; v < V; ++v) pf[v] = acc[k][v];
+                *reinterpret_cast<VT *>(red + (size_t)eidx[k] * SB + lq * V) = pv;
             }
         }
     }
     if (CS > 1) cluster.sync(); else __syncthreads();
     scd_stamp(P.dbg, 5);                          // partials exchanged
 
-    // ---- add the row-split partials in rank order, scale, write (coalesced along the detector) ----
+    // ---- add the row-split partials in rank order, scale, write ------------------------------
     const int per = (E + CS - 1) / CS;
     const int e_lo = rank * per, e_hi = min(E, e_lo + per);
     const int cnt = max(e_hi - e_lo, 0);
     const size_t sino_sz = (size_t)P.n_angles * n_det;
-    if (P.sino) {
-        for (int idx = tid; idx < cnt * SB; idx += NTHR) {
-            const int s = idx / cnt, e = e_lo + (idx - s * cnt);
-            float v;
-            if (CS > 1) {
-                v = 0.f;
-                for (int r = 0; r < CS; ++r) v += cluster.map_shared_rank(red, r)[(size_t)s * E + e];
-            } else {
-                v = red[(size_t)s * E + e];
-            }
-            if (b0 + s < P.batch) {
-                const int ai = e / n_det, j = e - ai * n_det;
-                P.sino[(size_t)(b0 + s) * sino_sz + (size_t)ang[ai].id * n_det + j] = v * ang[ai].scale;
-            }
-        }
-    }
     if (P.sino_il) {
-        // interleaved rows for the backprojector: samples fastest, zero bins either side
+        // interleaved rows for the backprojector (samples fastest, zero bins either side): one
+        // vector of V samples per thread and rank
         float *dst = P.sino_il + (size_t)grp * ((size_t)P.n_angles * P.il_nb * SB);
-        for (int idx = tid; idx < cnt * SB; idx += NTHR) {
-            const int el = idx / SB, s = idx - el * SB, e = e_lo + el;
-            float v;
-            if (CS > 1) {
-                v = 0.f;
-                for (int r = 0; r < CS; ++r) v += cluster.map_shared_rank(red, r)[(size_t)s * E + e];
-            } else {
-                v = red[(size_t)s * E + e];
+        for (int idx = tid; idx < cnt * LPR; idx += NTHR) {
+            const int el = idx / LPR, q = idx - el * LPR, e = e_lo + el;
+            float sum[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) sum[v] = 0.f;
+            for (int r = 0; r < CS; ++r) {
+                const float *src = (CS > 1 ? cluster.map_shared_rank(red, r) : red) + (size_t)e * SB + q * V;
+                const VT pv = *reinterpret_cast<const VT *>(src);
+                const float *pf = reinterpret_cast<const float *>(&pv);
+#pragma unroll
+                for (int v = 0; v < V; ++v) sum[v] += pf[v];
             }
             const int ai = e / n_det, j = e - ai * n_det;
-            dst[((size_t)ang[ai].id * P.il_nb + P.il_padl + j) * SB + s] = v * ang[ai].scale;
+            const float sc = ang[ai].scale;
+            VT ov;
+            float *of = reinterpret_cast<float *>(&ov);
+#pragma unroll
+            for (int v = 0; v < V; ++v) of[v] = sum[v] * sc;
+            *reinterpret_cast<VT *>(dst + ((size_t)ang[ai].id * P.il_nb + P.il_padl + j) * SB + q * V) = ov;
         }
         const int npad = P.il_nb - n_det;
         for (int ai = rank; ai < na; ai += CS) {
@@ -509,6 +505,18 @@ fp_march_kernel(const MqParams P)
                 const int jp = idx / SB, s = idx - jp * SB;
                 const int j = jp < P.il_padl ? jp : n_det + jp;
                 row[(size_t)j * SB + s] = 0.f;
+            }
+        }
+    }
+    if (P.sino) {
+        // user layout [sample][angle][bin]: consecutive threads -> consecutive bins (coalesced stores)
+        for (int idx = tid; idx < cnt * SB; idx += NTHR) {
+            const int s = idx / cnt, e = e_lo + (idx - s * cnt);
+            float v = 0.f;
+            for (int r = 0; r < CS; ++r) v += (CS > 1 ? cluster.map_shared_rank(red, r) : red)[(size_t)e * SB + s];
+            if (b0 + s < P.batch) {
+                const int ai = e / n_det, j = e - ai * n_det;
+                P.sino[(size_t)(b0 + s) * sino_sz + (size_t)ang[ai].id * n_det + j] = v * ang[ai].scale;
             }
         }
     }
@@ -651,7 +659,7 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
     nbuf = std::max(2, std::min(std::min(nbuf, MQ_MAX_NBUF), nstrips));
     while (nbuf > 1 && nbuf * strip + mq_fixed_smem(g, c.NA) > budget) --nbuf;
     c.nbuf = nbuf;
-    // the partials red[SB][NA*n_det] alias the ring
+    // the partials red[NA*n_det][SB] alias the ring
     c.ring_bytes = (std::max(nbuf * strip, (size_t)c.SB * c.NA * g->n_det * 4) + 127) & ~(size_t)127;
     c.smem = c.ring_bytes + mq_fixed_smem(g, c.NA);
     c.scratch_bytes = (size_t)c.groups * c.L.group_floats * 4;
