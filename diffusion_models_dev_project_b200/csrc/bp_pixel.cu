@@ -206,14 +206,10 @@ int scd_bp_ctas_per_sample_v1(const scd_geom *g, int batch)
 }
 
 template <int S, int WY>
-static int bp_launch_t(const BpParams &P, const BpConfig &c, cudaStream_t st)
+static int bp_launch_t(const BpParams &P, const BpConfig &c, cudaStream_t st, int device)
 {
-    static int configured_smem = 0;
-    if ((int)c.smem > configured_smem) {
-        SCD_CUDA(cudaFuncSetAttribute(bp_pixel_kernel<S, WY>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        configured_smem = (int)c.smem;
-    }
+    static ScdSmemAttr attr = {};        // per instantiation
+    SCD_CUDA(scd_ensure_smem(bp_pixel_kernel<S, WY>, attr, device, c.smem));
     bp_pixel_kernel<S, WY><<<c.grid, 32 * WY, c.smem, st>>>(P);
     SCD_LAUNCH_CHECK("bp_pixel_kernel");
     return 0;
@@ -236,7 +232,7 @@ int scd_launch_bp_v1(const scd_geom *g, const float *sino, float *out, int batch
     P.sino = sino; P.out = out; P.bp = g->d_bp;
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
     P.angle_lo = angle_lo; P.angle_hi = angle_hi; P.AC = c.AC; P.SEG = c.SEG; P.ep = ep;
-#define BP_CASE(SS, WW) if (c.S == SS && c.WY == WW) return bp_launch_t<SS, WW>(P, c, st);
+#define BP_CASE(SS, WW) if (c.S == SS && c.WY == WW) return bp_launch_t<SS, WW>(P, c, st, g->device);
     BP_CASE(1, 4) BP_CASE(1, 8) BP_CASE(1, 16)
     BP_CASE(2, 4) BP_CASE(2, 8) BP_CASE(2, 16)
     BP_CASE(4, 4) BP_CASE(4, 8) BP_CASE(4, 16)

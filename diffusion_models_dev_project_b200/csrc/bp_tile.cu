@@ -397,14 +397,10 @@ size_t scd_sino_il_bytes(const scd_geom *g, int batch)
 }
 
 template <int V, int LPR, int PPT>
-static int bq_launch_t(const BqParams &P, const BqConfig &c, cudaStream_t st)
+static int bq_launch_t(const BqParams &P, const BqConfig &c, cudaStream_t st, int device)
 {
-    static int configured_smem = -1;
-    if ((int)c.smem > configured_smem) {
-        SCD_CUDA(cudaFuncSetAttribute(bp_tile_kernel<V, LPR, PPT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
-        configured_smem = (int)c.smem;
-    }
+    static ScdSmemAttr attr = {};        // per instantiation
+    SCD_CUDA(scd_ensure_smem(bp_tile_kernel<V, LPR, PPT>, attr, device, c.smem));
     SCD_CUDA(scd_launch_kernel(bp_tile_kernel<V, LPR, PPT>, c.grid, dim3(BQ_THREADS), c.smem, st, 0, P));
     SCD_LAUNCH_CHECK("bp_tile_kernel");
     return 0;
@@ -427,7 +423,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     P.ep = ep; P.dbg = scd_debug_stamps();
     const int WY = BQ_NW / c.LPR;
     (void)WY;
-#define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st);
+#define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st, g->device);
     BQ_CASE(1, 1, 1) BQ_CASE(1, 1, 2) BQ_CASE(2, 1, 1) BQ_CASE(2, 1, 2) BQ_CASE(4, 1, 1) BQ_CASE(4, 1, 2)
     BQ_CASE(4, 2, 1) BQ_CASE(4, 2, 2) BQ_CASE(4, 2, 4) BQ_CASE(4, 4, 2) BQ_CASE(4, 4, 4)
 #undef BQ_CASE

@@ -509,9 +509,14 @@ fp_march_kernel(const MqParams P)
         }
     }
     if (P.sino) {
-        // user layout [sample][angle][bin]: consecutive threads -> consecutive bins (coalesced stores)
-        for (int idx = tid; idx < cnt * SB; idx += NTHR) {
-            const int s = idx / cnt, e = e_lo + (idx - s * cnt);
+        // user layout [sample][angle][bin]: 8 consecutive lanes take 8 consecutive bins of one sample
+        // (one full 32-byte sector per store), the next 8 lanes the next sample (shared-memory reads
+        // of red[e][s] then conflict at most SB/4-fold)
+        const int nblk = (cnt + 7) >> 3;
+        for (int idx = tid; idx < nblk * 8 * SB; idx += NTHR) {
+            const int blk = idx / (8 * SB), rem = idx - blk * (8 * SB);
+            const int s = rem >> 3, e = e_lo + blk * 8 + (rem & 7);
+            if (e >= e_hi) continue;
             float v = 0.f;
             for (int r = 0; r < CS; ++r) v += (CS > 1 ? cluster.map_shared_rank(red, r) : red)[(size_t)e * SB + s];
             if (b0 + s < P.batch) {
@@ -762,14 +767,10 @@ size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch)
 }
 
 template <int V, int LPR, int NSLOT, int TR, int NWT>
-static int mq_launch_t(const MqParams &P, dim3 grid, size_t smem, cudaStream_t st)
+static int mq_launch_t(const MqParams &P, dim3 grid, size_t smem, cudaStream_t st, int device)
 {
-    static int configured_smem = -1;     // per instantiation
-    if ((int)smem > configured_smem) {
-        SCD_CUDA(cudaFuncSetAttribute(fp_march_kernel<V, LPR, NSLOT, TR, NWT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured_smem = (int)smem;
-    }
+    static ScdSmemAttr attr = {};        // per instantiation
+    SCD_CUDA(scd_ensure_smem(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, attr, device, smem));
     SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P));
     SCD_LAUNCH_CHECK("fp_march_kernel");
     return 0;
@@ -816,7 +817,19 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
         SCD_LAUNCH_CHECK("fp_packq_kernel");
     }
 
-    const MqPlan pl = mq_plan(g, c, angle_lo, angle_hi);
+    // the plan depends only on the geometry, the configuration and the angle range: keep the last one
+    // (the search simulates a few hundred schedules, too slow to repeat at every launch)
+    struct PlanKey { const scd_geom *g; int lo, hi, groups, NA, CS, plan, sm; };
+    static thread_local PlanKey last_key = {nullptr, 0, 0, 0, 0, 0, 0, 0};
+    static thread_local MqPlan last_plan;
+    const PlanKey key = {g, angle_lo, angle_hi, c.groups, c.NA, c.CS, g->tune_fp_plan, g->sm_count};
+    const bool same = key.g == last_key.g && key.lo == last_key.lo && key.hi == last_key.hi && key.groups == last_key.groups &&
+                      key.NA == last_key.NA && key.CS == last_key.CS && key.plan == last_key.plan && key.sm == last_key.sm;
+    if (!same) {
+        last_plan = mq_plan(g, c, angle_lo, angle_hi);
+        last_key = key;
+    }
+    const MqPlan &pl = last_plan;
     if (pl.units == 0) return 0;
     if ((long)pl.units * c.groups * c.CS > 0x7fffffffL) { scd_set_error("scd_fp: too many CTAs"); return SCD_E_INVALID; }
     P.groups = c.groups; P.n_big = pl.n_big; P.n_units = pl.units; P.dbg = scd_debug_stamps();
@@ -826,16 +839,16 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     int rc = SCD_E_INVALID;
 #define MQ_CASE(VV, LL, TT)                                                                         \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 16)                                      \
-        rc = c.NSLOT == 6 ? mq_launch_t<VV, LL, 6, TT, 16>(P, grid, c.smem, st)                     \
-                          : mq_launch_t<VV, LL, 13, TT, 16>(P, grid, c.smem, st);
+        rc = c.NSLOT == 6 ? mq_launch_t<VV, LL, 6, TT, 16>(P, grid, c.smem, st, g->device)                     \
+                          : mq_launch_t<VV, LL, 13, TT, 16>(P, grid, c.smem, st, g->device);
 #define MQ_CASE24(VV, LL, TT)                                                                       \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 24)                                      \
-        rc = c.NSLOT == 4 ? mq_launch_t<VV, LL, 4, TT, 24>(P, grid, c.smem, st)                     \
-                          : mq_launch_t<VV, LL, 8, TT, 24>(P, grid, c.smem, st);
+        rc = c.NSLOT == 4 ? mq_launch_t<VV, LL, 4, TT, 24>(P, grid, c.smem, st, g->device)                     \
+                          : mq_launch_t<VV, LL, 8, TT, 24>(P, grid, c.smem, st, g->device);
 #define MQ_CASE32(VV, LL, TT)                                                                       \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 32)                                      \
-        rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, grid, c.smem, st)                     \
-                          : mq_launch_t<VV, LL, 6, TT, 32>(P, grid, c.smem, st);
+        rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, grid, c.smem, st, g->device)                     \
+                          : mq_launch_t<VV, LL, 6, TT, 32>(P, grid, c.smem, st, g->device);
     MQ_CASE(1, 1, 8) MQ_CASE(2, 1, 8) MQ_CASE(4, 1, 8) MQ_CASE(4, 1, 4)
     MQ_CASE(4, 2, 8) MQ_CASE(4, 2, 4) MQ_CASE(4, 4, 4) MQ_CASE(4, 4, 2)
     MQ_CASE24(4, 1, 8) MQ_CASE24(4, 1, 4) MQ_CASE24(4, 2, 8) MQ_CASE24(4, 2, 4) MQ_CASE24(4, 4, 4) MQ_CASE24(4, 4, 2)

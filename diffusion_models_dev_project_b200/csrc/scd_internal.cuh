@@ -67,6 +67,19 @@ static inline cudaError_t scd_launch_kernel(void (*kernel)(KArgs...), dim3 grid,
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Opt-in dynamic shared memory is a per-device function attribute: remember, per device, the
+// largest size a kernel instantiation has been configured for.
+struct ScdSmemAttr { int configured[16]; };
+template <typename K>
+static inline cudaError_t scd_ensure_smem(K kernel, ScdSmemAttr &state, int device, size_t smem)
+{
+    const int slot = device >= 0 && device < 16 ? device : 0;
+    if ((int)smem <= state.configured[slot] && device < 16) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) state.configured[slot] = (int)smem;
+    return e;
+}
+
 // -------------------------------------------------------------- geometry ---
 // Forward projector, per angle.  In "tile coordinates" the ray of detector bin
 // j crosses marching row r at interpolation-axis position
