@@ -380,7 +380,7 @@ static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_
     return c;
 }
 
-int scd_bp_ctas_per_sample_v2(const scd_geom *g, int batch)
+int scd_bp_ctas_per_sample(const scd_geom *g, int batch)
 {
     BqConfig c = bq_choose(g, batch, 0, g->n_angles);
     return (int)(c.grid.x * c.grid.y);
@@ -445,8 +445,7 @@ int scd_launch_sino_pack(const scd_geom *g, const float *sino, float *sino_il, i
     return 0;
 }
 
-// ------------------------------------------------------------ dispatcher ---
-// bp_impl tuning knob: 0 / 2 = this kernel, 1 = the previous generation (bp_pixel.cu), kept for A/B runs
+// ----------------------------------------------------- user-layout entry ---
 int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
                   int angle_lo, int angle_hi, const BpEpilogue &ep, void *scratch, size_t scratch_bytes,
                   cudaStream_t st)
@@ -459,7 +458,6 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
         return SCD_E_INVALID;
     }
     if (batch == 0) return 0;
-    if (g->tune_bp_impl == 1) return scd_launch_bp_v1(g, sino, out, batch, angle_lo, angle_hi, ep, st);
     const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
     const size_t need = scd_sino_il_bytes(g, batch) - 256;
     if (!scratch || sp + need > (uintptr_t)scratch + scratch_bytes) {
@@ -472,15 +470,9 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
     return scd_launch_bp_il(g, (const float *)sp, out, batch, angle_lo, angle_hi, ep, st);
 }
 
-int scd_bp_ctas_per_sample(const scd_geom *g, int batch)
-{
-    return g->tune_bp_impl == 1 ? scd_bp_ctas_per_sample_v1(g, batch) : scd_bp_ctas_per_sample_v2(g, batch);
-}
-
 int scd_bp_ctas_per_sample_max(const scd_geom *g, int batch)
 {
-    // workspace sizing: independent of the tuning knobs
-    int n = scd_bp_ctas_per_sample_v1(g, batch);
-    n = std::max(n, ((g->n1 + 31) / 32) * ((g->n0 + 7) / 8));
-    return n;
+    // workspace sizing: independent of the tuning knobs (smallest tile = 32 x 8 pixels)
+    (void)batch;
+    return ((g->n1 + 31) / 32) * ((g->n0 + 7) / 8);
 }

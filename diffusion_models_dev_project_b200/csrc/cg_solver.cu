@@ -7,8 +7,8 @@
 //   repeat n_iter: d = op(p); alpha = rr/<p,d>; x += alpha p; r -= alpha d;
 //                  rr' = ||r||^2; beta = rr'/rr; p = r + beta p
 // with op(v) = v + gamma*A*(A v) (src/samplers/utils.py:188-189).
-// Launches per iteration: fp_joseph, bp_pixel(+axpy,+<p,d>), cg_update_xr,
-// cg_update_p (the last p-update is skipped: its result is never read).
+// Launches per iteration: fp_packq (p-update fused), fp_march, bp_tile(+axpy,+<p,d>), cg_update_xr
+// (the last p-update is skipped: its result is never read).
 #include "scd_internal.cuh"
 #include <algorithm>
 #include <cstring>
@@ -29,9 +29,8 @@ static CgLayout cg_layout(const scd_geom *g, int batch)
     const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
     L.part_stride = (size_t)std::max(nbp, nvec);
     size_t o = 0;
-    // q = A p lives in the sample-interleaved layout the backprojector stages from (or in the
-    // user layout when the previous-generation backprojector is selected): room for either
-    L.off_q = o;  o += align256(std::max(L.sino * batch * 4, scd_sino_il_bytes(g, batch)));
+    // q = A p lives in the sample-interleaved layout the backprojector stages from
+    L.off_q = o;  o += align256(scd_sino_il_bytes(g, batch));
     L.off_r = o;  o += align256(L.img * batch * 4);
     L.off_p = o;  o += align256(L.img * batch * 4);
     L.off_d = o;  o += align256(L.img * batch * 4);
@@ -74,11 +73,9 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
     const float gs = gamma * (float)g->adj_scale;
     int rc;
-    const bool il = g->tune_bp_impl != 1;          // q in the interleaved layout
-    float *q_user = il ? nullptr : q, *q_il = il ? q : nullptr;
+    float *q_user = nullptr, *q_il = q;            // q = A p: interleaved layout only
     auto bp = [&](float *out, const BpEpilogue &e) {
-        return il ? scd_launch_bp_il(g, q, out, batch, 0, g->n_angles, e, st)
-                  : scd_launch_bp_v1(g, q, out, batch, 0, g->n_angles, e, st);
+        return scd_launch_bp_il(g, q, out, batch, 0, g->n_angles, e, st);
     };
 
     // r = rhs - x - gamma A*(A x);  p = r;  rr = ||r||^2

@@ -178,12 +178,9 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_threads")) g->tune_fp_threads = value;
     else if (!strcmp(key, "fp_nbuf")) g->tune_fp_nbuf = value;
     else if (!strcmp(key, "fp_cluster")) g->tune_fp_cluster = value;
-    else if (!strcmp(key, "fp_impl")) g->tune_fp_impl = value;
     else if (!strcmp(key, "fp_plan")) g->tune_fp_plan = value;
     else if (!strcmp(key, "fp_skip_pack")) g->tune_fp_skip_pack = value;
-    else if (!strcmp(key, "bp_samples")) g->tune_bp_samples = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
-    else if (!strcmp(key, "bp_impl")) g->tune_bp_impl = value;
     else { scd_set_error("scd_set_tuning: unknown key '%s'", key); return SCD_E_INVALID; }
     return 0;
 }

@@ -114,8 +114,8 @@ struct scd_geom {
     int     *h_order;
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
-    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_impl, tune_fp_plan, tune_fp_skip_pack;
-    int tune_bp_samples, tune_bp_tile, tune_bp_impl;
+    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan, tune_fp_skip_pack;
+    int tune_bp_tile;
     // sample-interleaved sinogram rows (bp_tile.cu): il_padl zero bins, n_det bins, zero bins up to il_nb
     int il_padl, il_nb;
 };
@@ -164,8 +164,6 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
                   cudaStream_t st);
 int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int batch,
                      int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st);
-int scd_launch_bp_v1(const scd_geom *g, const float *sino, float *out, int batch,
-                     int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st);
 int scd_launch_sino_pack(const scd_geom *g, const float *sino, float *sino_il, int batch,
                          int angle_lo, int angle_hi, cudaStream_t st);
 size_t scd_sino_il_bytes(const scd_geom *g, int batch);
@@ -173,8 +171,6 @@ size_t scd_sino_il_bytes(const scd_geom *g, int batch);
 // an upper bound independent of the tuning (workspace sizing)
 int scd_bp_ctas_per_sample(const scd_geom *g, int batch);
 int scd_bp_ctas_per_sample_max(const scd_geom *g, int batch);
-int scd_bp_ctas_per_sample_v1(const scd_geom *g, int batch);
-int scd_bp_ctas_per_sample_v2(const scd_geom *g, int batch);
 
 // Vector kernels of the CG recurrences (vec_ops.cu).  *_part arrays hold
 // per-block partial sums [batch][part_stride]; consumers add them in index
@@ -185,10 +181,6 @@ int scd_launch_cg_update_xr(const float *x_in, float *x, float *r, const float *
                             const float *pd_part, int pd_n, int part_stride,
                             float *rr_new_part, int batch, int64_t numel,
                             cudaStream_t st);
-int scd_launch_cg_update_p(float *p, const float *r, const float *rr_new_part,
-                           int rr_new_n, const float *rr_old_part, int rr_old_n,
-                           int part_stride, int batch, int64_t numel,
-                           cudaStream_t st);
 int scd_launch_tweedie_rhs(const float *x, const float *s, const float *atb,
                            const float *t, const float *abar, int n_table,
                            float gamma, float *xhat0, float *b, int batch,

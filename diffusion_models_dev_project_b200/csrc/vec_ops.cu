@@ -1,8 +1,8 @@
 // K3/K4/K5  HBM-bound vector kernels of the data-consistency step.
 //
 //   cg_update_xr : alpha = rr/pd;  x += alpha p;  r -= alpha d;  partial ||r||^2
-//   cg_update_p  : beta = rr_new/rr_old;  p = r + beta p
-//                  (reference src/utils/cg.py:29-38)
+//                  (reference src/utils/cg.py:29-33; the direction update p = r + beta p of :35-38 is
+//                  fused into the pack pass of the projector, fp_march.cu)
 //   tweedie_rhs  : xhat0 = (x - s*std_t)/mean_t;  b = xhat0 + gamma*atb
 //                  (reference src/samplers/utils.py:370-378 and :197)
 //   ddim         : DDPM branch of ddim() (reference src/samplers/utils.py:356-368)
@@ -121,39 +121,6 @@ cg_update_xr_kernel(const float *x_in, float *x, float *__restrict__ r,
     }
     const float tot = block_sum(acc, red);
     if (threadIdx.x == 0) rr_new_part[(size_t)b * part_stride + blockIdx.x] = tot;
-}
-
-template <bool VEC4>
-__global__ void __launch_bounds__(VEC_THREADS)
-cg_update_p_kernel(float *__restrict__ p, const float *__restrict__ r,
-                   const float *__restrict__ rr_new_part, int rr_new_n,
-                   const float *__restrict__ rr_old_part, int rr_old_n,
-                   int part_stride, int64_t numel)
-{
-    scd_pdl_wait();                               // predecessor complete, its writes visible
-    scd_pdl_trigger();
-    __shared__ float sc[2];
-    const int b = blockIdx.y;
-    const float rn = sum_partials(rr_new_part + (size_t)b * part_stride, rr_new_n, &sc[0]);
-    const float ro = sum_partials(rr_old_part + (size_t)b * part_stride, rr_old_n, &sc[1]);
-    const float beta = __fdiv_rn(rn, ro);
-    int64_t lo, hi;
-    slice_of(numel, lo, hi);
-    const size_t base = (size_t)b * numel;
-    if (VEC4) {
-        float4 *p4 = reinterpret_cast<float4 *>(p + base);
-        const float4 *r4 = reinterpret_cast<const float4 *>(r + base);
-        for (int64_t i = (lo >> 2) + threadIdx.x; i < (hi >> 2); i += VEC_THREADS) {
-            float4 pv = p4[i];
-            const float4 rv = r4[i];
-            pv.x = fmaf(beta, pv.x, rv.x); pv.y = fmaf(beta, pv.y, rv.y);
-            pv.z = fmaf(beta, pv.z, rv.z); pv.w = fmaf(beta, pv.w, rv.w);
-            p4[i] = pv;
-        }
-    } else {
-        for (int64_t i = lo + threadIdx.x; i < hi; i += VEC_THREADS)
-            p[base + i] = fmaf(beta, p[base + i], r[base + i]);
-    }
 }
 
 // ---- schedule look-up: abar[t+1] exactly like DDPM._compute_alpha_cumprod ----
@@ -287,22 +254,6 @@ int scd_launch_cg_update_xr(const float *x_in, float *x, float *r, const float *
         SCD_CUDA(scd_launch_kernel(cg_update_xr_kernel<false>, grid, dim3(VEC_THREADS), 0, st, 0, x_in, x, r, p, d, rr_part, rr_n, pd_part, pd_n,
                                                                 part_stride, rr_new_part, numel));
     SCD_LAUNCH_CHECK("cg_update_xr_kernel");
-    return 0;
-}
-
-int scd_launch_cg_update_p(float *p, const float *r, const float *rr_new_part, int rr_new_n,
-                           const float *rr_old_part, int rr_old_n, int part_stride, int batch,
-                           int64_t numel, cudaStream_t st)
-{
-    if (batch <= 0 || numel <= 0) return 0;
-    dim3 grid(scd_vec_blocks_per_sample(numel, batch), batch);
-    if (vec4_ok(numel, p, r))
-        SCD_CUDA(scd_launch_kernel(cg_update_p_kernel<true>, grid, dim3(VEC_THREADS), 0, st, 0, p, r, rr_new_part, rr_new_n, rr_old_part,
-                                                              rr_old_n, part_stride, numel));
-    else
-        SCD_CUDA(scd_launch_kernel(cg_update_p_kernel<false>, grid, dim3(VEC_THREADS), 0, st, 0, p, r, rr_new_part, rr_new_n, rr_old_part,
-                                                               rr_old_n, part_stride, numel));
-    SCD_LAUNCH_CHECK("cg_update_p_kernel");
     return 0;
 }
 

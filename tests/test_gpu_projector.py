@@ -1,4 +1,4 @@
-"""GPU parity of A (fp_joseph) and A* (bp_pixel) against the CPU oracle, through the C ABI.
+"""GPU parity of A (fp_packq + fp_march) and A* (sino_pack + bp_tile) against the CPU oracle, through the C ABI.
 
 Tolerance: 1e-4 relative L2 (BASELINE.json north_star); observed values are ~1e-6.
 """
@@ -80,8 +80,7 @@ def test_fp_bp_other_shapes(im_shape, num_angles):
                                   dict(fp_samples=1, bp_tile=32), dict(fp_samples=2, bp_tile=16), dict(fp_samples=4, bp_tile=32),
                                   dict(fp_samples=8, bp_tile=32), dict(fp_samples=8, bp_tile=16), dict(fp_samples=8, bp_tile=8), dict(fp_samples=16, bp_tile=8), dict(fp_samples=16),
                                   dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_threads=768), dict(fp_samples=8, fp_angles=3, fp_rows=8, fp_threads=768, fp_cluster=2), dict(fp_samples=4, fp_threads=768),
-                                  dict(bp_impl=1, bp_samples=2, bp_tile=16), dict(bp_impl=1, bp_samples=4, bp_tile=64),
-                                  dict(bp_impl=1, bp_samples=1, bp_tile=32)])
+                                  dict(fp_samples=4, bp_tile=16), dict(fp_samples=2, bp_tile=32)])
 def test_tuning_variants_agree(tune):
     """Every template instantiation (samples per thread, rays per thread, tile shape) computes the same thing."""
     geom = O.OracleGeometry((96, 96), 20)

@@ -48,7 +48,7 @@ def main():
     nbytes = 4 * (a.im * a.im + rt.obs_shape[0] * rt.obs_shape[1]) * a.batch
 
     def run(tune):
-        keys = ['fp_impl', 'fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'bp_samples', 'bp_tile', 'bp_impl']
+        keys = ['fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'bp_tile']
         rt.set_tuning(dev, **{k: tune.get(k, 0) for k in keys})
         if a.kernel == 'fp':
             fn = lambda: rt._fp(x)          # noqa: E731
@@ -77,7 +77,6 @@ def main():
                     continue
                 run(dict(fp_samples=SB, fp_angles=NA, fp_rows=TR, fp_cluster=CS, fp_threads=TH))
         elif a.kernel == 'bp':
-            run(dict(bp_impl=1))
             run(dict())
             for SB, T in itertools.product([4, 8, 16], [8, 16, 32]):
                 if SB > max(4, a.batch):

@@ -9,7 +9,7 @@ import sys
 
 OURS = ('fp_packq_kernel', 'fp_march_kernel', 'bp_tile_kernel', 'sino_pack_kernel', 'cg_update_xr_kernel',
         'cg_update_p_kernel', 'tweedie_rhs_kernel', 'ddim_kernel', 'residual_sq_kernel', 'tv_fwd_kernel',
-        'tv_grad_kernel', 'bp_pixel_kernel')
+        'tv_grad_kernel')
 
 
 def main(path):
