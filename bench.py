@@ -38,7 +38,7 @@ BYTES = {
     'bp_tile': 4 * (IM * IM + ANGLES * NDET),
     'bp_tile_axpy_dot': 4 * (2 * IM * IM + ANGLES * NDET),      # + read of the addend
     'cg_update_xr': 6 * 4 * IM * IM,
-    'cg_update_p': 3 * 4 * IM * IM,
+    'cg_direction_update': 3 * 4 * IM * IM,        # p = r + beta p (fused into the pack pass)
     'tweedie_rhs': 5 * 4 * IM * IM,
     'ddim': 4 * 4 * IM * IM,
 }
@@ -284,7 +284,7 @@ def kernel_sweep(rt, batch, dev, hbm_peak, iters=20):
         cg(op, x, p, CG_ITER)
     ms = cuda_time(lambda: cg(op, x, p, CG_ITER), iters, flush)
     cg_bytes = (CG_ITER + 1) * (BYTES['fp_march'] + BYTES['bp_tile_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
-        + (CG_ITER - 1) * BYTES['cg_update_p']
+        + (CG_ITER - 1) * BYTES['cg_direction_update']
     gbs = cg_bytes * batch / (ms * 1e-3) / 1e9
     out['cg_solve_k5'] = {'ms': ms, 'GB/s': gbs, 'frac_hbm': gbs / hbm_peak}
     del flush
@@ -402,7 +402,7 @@ def run_b200(args):
     dc_launches = fused.launch_count()
     ms_dc = cuda_time(dc_only, 20)
     dc_bytes = (CG_ITER + 1) * (BYTES['fp_march'] + BYTES['bp_tile_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
-        + (CG_ITER - 1) * BYTES['cg_update_p'] + BYTES['tweedie_rhs'] + BYTES['ddim']
+        + (CG_ITER - 1) * BYTES['cg_direction_update'] + BYTES['tweedie_rhs'] + BYTES['ddim']
 
     line = None
     if rank == 0:

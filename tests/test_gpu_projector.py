@@ -205,6 +205,39 @@ def test_linearity_and_dot_product_full_size():
     assert abs(lhs - rhs) / abs(rhs) < 2e-3
 
 
+def test_full_size_batch_independence_and_angle_shards():
+    """BASELINE config 3 / 4 sizes through size-independent properties: a sample's result does not depend on
+    the batch it travels in (256 samples vs alone), and the angle shards of the 501^2 / 1200-angle operator
+    add up to the whole."""
+    rt = _rt((256, 256), 60)
+    gen = torch.Generator(device='cuda').manual_seed(9)
+    x = torch.rand(256, 1, 256, 256, device='cuda', generator=gen)
+    y = rt(x)
+    z = rt.trafo_adjoint(y)
+    for i in (0, 100, 255):
+        yi = rt(x[i:i + 1])
+        assert float((yi - y[i:i + 1]).norm() / yi.norm()) < 1e-6
+        zi = rt.trafo_adjoint(y[i:i + 1])
+        assert float((zi - z[i:i + 1]).norm() / zi.norm()) < 1e-6
+    nz = rt.normal_apply(x, 0.01)
+    assert float((nz - (x + 0.01 * z)).norm() / nz.norm()) < 1e-6
+    del x, y, z, nz
+    big = _rt((501, 501), 1200)
+    xs = torch.rand(2, 1, 501, 501, device='cuda', generator=gen)
+    ys = big(xs)
+    full = big.trafo_adjoint(ys)
+    acc = torch.zeros_like(full)
+    for r in range(8):                                    # the 8-GPU sharding of config 4, on one device
+        lo, hi = r * 150, (r + 1) * 150
+        part = big._fp(xs, angle_range=(lo, hi))
+        assert float((part[..., lo:hi, :] - ys[..., lo:hi, :]).norm() / ys[..., lo:hi, :].norm()) < 1e-6
+        acc += big._bp(ys, big.adj_scale, angle_range=(lo, hi))
+    assert float((acc - full).norm() / full.norm()) < 1e-6
+    # A*(1) = pi inside the field of view also at this size
+    ones = torch.ones(1, 1, 1200, big.obs_shape[1], device='cuda')
+    assert torch.allclose(big.trafo_adjoint(ones), torch.full((1, 1, 501, 501), float(np.pi), device='cuda'), rtol=2e-5)
+
+
 def test_flat_interface_and_shapes():
     rt = _rt((64, 64), 10)
     x = torch.rand(2, 3, 64, 64, device='cuda')
