@@ -614,7 +614,7 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
         const int units4 = c.groups * ((n_cls_max + 3) / 4) * 2;
         if (units4 * 4 <= 2 * g->sm_count) c.NWT = 24;
     }
-    if (g->tune_fp_threads == 1024 && c.V == 4) c.NWT = 32;
+    if (g->tune_fp_threads == 1024 && c.V == 4 && c.LPR >= 2) c.NWT = 32;
     else if (g->tune_fp_threads == 768 && c.V == 4) c.NWT = 24;
     else if (g->tune_fp_threads == 512) c.NWT = 16;
     const int NW = c.NWT - 1;
