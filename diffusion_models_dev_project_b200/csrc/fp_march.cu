@@ -55,6 +55,7 @@ struct MqParams {
     float         *sino_il;  // interleaved layout [group][n_angles][il_nb][SB] (bp_tile.cu) or NULL
     float         *packed;
     const FpAngle *fp;
+    const float2  *rayt;     // [n_angles][n_det] (u0 + 1, b) per ray
     const int     *order;
     int n0, n1, n_angles, n_det, batch;
     int NA;                  // largest number of angles per CTA (sizes the tables)
@@ -92,8 +93,30 @@ fp_packq_kernel(const MqParams P, const FpPrologue Q)
     const int K0 = blockIdx.y * PK_T, K1 = blockIdx.x * PK_T;
     const size_t isz = (size_t)P.n0 * P.n1;
 
+    // thread = pixel; four samples per round, their loads issued together (memory-level parallelism)
+    const int ty = tid >> 4, tx = tid & 15;
+    const int k0 = K0 + ty, k1 = K1 + tx;
+    const bool in_img = k0 < P.n0 && k1 < P.n1;
+    float a[4], c[4], e[4];
+    bool live[4];
+    auto load_round = [&](int s0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int s = s0 + i, b = grp * SB + s;
+            live[i] = in_img && s < SB && b < P.batch;
+            a[i] = c[i] = e[i] = 0.f;
+            if (live[i]) {
+                const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
+                if (MODE == 0) a[i] = __ldg(P.img + o);
+                else if (MODE == 1) { a[i] = Q.p[o]; c[i] = Q.r[o]; }
+                else { a[i] = Q.x[o]; c[i] = Q.s[o]; e[i] = Q.atb[o]; }
+            }
+        }
+    };
+    load_round(0);                                // in flight while the per-sample scalars are formed
+
     if (MODE != 0) {
-        // per-sample scalars, one warp per sample (8 warps, SB <= 32 samples)
+        // per-sample scalars, one warp per sample (8 warps, SB <= 16 samples)
         const int w = tid >> 5, lane = tid & 31;
         for (int s = w; s < SB; s += 8) {
             const int b = grp * SB + s;
@@ -120,28 +143,11 @@ fp_packq_kernel(const MqParams P, const FpPrologue Q)
         __syncthreads();
     }
 
-    // ---- produce the tile: thread = pixel, loop over the samples of the group ----
+    // ---- produce the tile ----
     {
-        const int ty = tid >> 4, tx = tid & 15;
-        const int k0 = K0 + ty, k1 = K1 + tx;
-        const bool in_img = k0 < P.n0 && k1 < P.n1;
         float *tp = tile + (ty * (PK_T + 1) + tx) * SBP;
-        // four samples per round: their loads are issued together (memory-level parallelism)
         for (int s0 = 0; s0 < SB; s0 += 4) {
-            float a[4], c[4], e[4];
-            bool live[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int s = s0 + i, b = grp * SB + s;
-                live[i] = in_img && s < SB && b < P.batch;
-                a[i] = c[i] = e[i] = 0.f;
-                if (live[i]) {
-                    const size_t o = b * isz + (size_t)k0 * P.n1 + k1;
-                    if (MODE == 0) a[i] = __ldg(P.img + o);
-                    else if (MODE == 1) { a[i] = Q.p[o]; c[i] = Q.r[o]; }
-                    else { a[i] = Q.x[o]; c[i] = Q.s[o]; e[i] = Q.atb[o]; }
-                }
-            }
+            if (s0 > 0) load_round(s0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int s = s0 + i, b = grp * SB + s;
@@ -356,13 +362,13 @@ fp_march_kernel(const MqParams P)
         for (int i = 0; i < NBUF; ++i) { mq_mbar_init(&full[i], 1); mq_mbar_init(&empty[i], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    // ray table of this unit: zf = u + 1 (left pad pixel) at row 0 and the slope per row, both
+    // evaluated in fp64 at geometry creation (constant data: read before the PDL wait)
     for (int e = tid; e < E; e += NTHR) {
         const int ai = e / n_det, j = e - ai * n_det;
-        const int id = P.order[pos0 + ai];
-        const FpAngle f = P.fp[id];
-        // zf = u + 1 (left pad pixel): floor(zf) = packed pixel of the left tap
-        rays[e] = make_float2((float)(f.a * (double)j + (f.c + 1.0)), (float)f.b);
-        if (j == 0) { MqAng a; a.scale = f.scale; a.id = id; ang[ai] = a; }
+        const int id = __ldg(P.order + pos0 + ai);
+        rays[e] = __ldg(P.rayt + (size_t)id * n_det + j);
+        if (j == 0) { MqAng a; a.scale = P.fp[id].scale; a.id = id; ang[ai] = a; }
     }
     __syncthreads();                              // mbarrier init + tables visible
     scd_stamp(P.dbg, 1);                          // tables done
@@ -795,7 +801,7 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     }
     MqParams P;
     memset(&P, 0, sizeof(P));
-    P.img = img; P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb; P.packed = (float *)sp; P.fp = g->d_fp; P.order = g->d_order;
+    P.img = img; P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb; P.packed = (float *)sp; P.fp = g->d_fp; P.rayt = g->d_rayt; P.order = g->d_order;
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
     P.NA = c.NA; P.nbuf = c.nbuf; P.CS = c.CS; P.rows_per_cta = c.rows_per_cta; P.ring_bytes = (int)c.ring_bytes; P.L = c.L;
     P.need_cls[0] = ncls[0] > 0; P.need_cls[1] = ncls[1] > 0;

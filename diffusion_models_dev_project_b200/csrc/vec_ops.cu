@@ -87,8 +87,20 @@ cg_update_xr_kernel(const float *x_in, float *x, float *__restrict__ r,
     __shared__ float red[VEC_THREADS / 32];
     __shared__ float sc[2];
     const int b = blockIdx.y;
-    const float rr = sum_partials(rr_part + (size_t)b * part_stride, rr_n, &sc[0]);
-    const float pd = sum_partials(pd_part + (size_t)b * part_stride, pd_n, &sc[1]);
+    // ||r||^2 and <p,d> from their per-block partials: warp 0 and warp 1 add them concurrently (each in
+    // the fixed lane-strided + butterfly order of sum_partials), one barrier for both
+    if (threadIdx.x < 64) {
+        const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const float *part = (w == 0 ? rr_part : pd_part) + (size_t)b * part_stride;
+        const int n = w == 0 ? rr_n : pd_n;
+        float v = 0.f;
+        for (int i = lane; i < n; i += 32) v += part[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) sc[w] = v;
+    }
+    __syncthreads();
+    const float rr = sc[0], pd = sc[1];
     const float alpha = __fdiv_rn(rr, pd);      // no guard: same as the reference
     int64_t lo, hi;
     slice_of(numel, lo, hi);
