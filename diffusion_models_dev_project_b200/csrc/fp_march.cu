@@ -55,7 +55,8 @@ struct MqParams {
     float         *sino_il;  // interleaved layout [group][n_angles][il_nb][SB] (bp_tile.cu) or NULL
     float         *packed;
     const FpAngle *fp;
-    const float2  *rayt;     // [n_angles][n_det] (u0 + 1, b) per ray
+    const float2  *rayt;     // [order position][n_det] (u0 + 1, b) per ray
+    const float2  *angt;     // [order position] (scale, angle id bits)
     const int     *order;
     int n0, n1, n_angles, n_det, batch;
     int NA;                  // largest number of angles per CTA (sizes the tables)
@@ -364,11 +365,10 @@ fp_march_kernel(const MqParams P)
     }
     // ray table of this unit: zf = u + 1 (left pad pixel) at row 0 and the slope per row, both
     // evaluated in fp64 at geometry creation (constant data: read before the PDL wait)
-    for (int e = tid; e < E; e += NTHR) {
-        const int ai = e / n_det, j = e - ai * n_det;
-        const int id = __ldg(P.order + pos0 + ai);
-        rays[e] = __ldg(P.rayt + (size_t)id * n_det + j);
-        if (j == 0) { MqAng a; a.scale = P.fp[id].scale; a.id = id; ang[ai] = a; }
+    for (int e = tid; e < E; e += NTHR) rays[e] = __ldg(P.rayt + (size_t)pos0 * n_det + e);
+    if (tid < na) {
+        const float2 t = __ldg(P.angt + pos0 + tid);
+        MqAng a; a.scale = t.x; a.id = __float_as_int(t.y); ang[tid] = a;
     }
     __syncthreads();                              // mbarrier init + tables visible
     scd_stamp(P.dbg, 1);                          // tables done
@@ -801,7 +801,7 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     }
     MqParams P;
     memset(&P, 0, sizeof(P));
-    P.img = img; P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb; P.packed = (float *)sp; P.fp = g->d_fp; P.rayt = g->d_rayt; P.order = g->d_order;
+    P.img = img; P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb; P.packed = (float *)sp; P.fp = g->d_fp; P.rayt = g->d_rayt; P.angt = g->d_angt; P.order = g->d_order;
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
     P.NA = c.NA; P.nbuf = c.nbuf; P.CS = c.CS; P.rows_per_cta = c.rows_per_cta; P.ring_bytes = (int)c.ring_bytes; P.L = c.L;
     P.need_cls[0] = ncls[0] > 0; P.need_cls[1] = ncls[1] > 0;

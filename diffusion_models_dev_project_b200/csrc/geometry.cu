@@ -133,15 +133,23 @@ extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
     std::copy(c0.begin(), c0.end(), g->h_order);
     std::copy(c1.begin(), c1.end(), g->h_order + c0.size());
 
-    // per-ray start position and slope of the forward march, evaluated in fp64 once
-    std::vector<float2> rayt((size_t)na * d->n_det);
-    for (int i = 0; i < na; ++i)
+    // per-ray start position and slope of the forward march, evaluated in fp64 once; both tables are
+    // stored in order[] order so that a CTA reads them without first looking the angle id up
+    std::vector<float2> rayt((size_t)na * d->n_det), angt((size_t)na);
+    for (int p = 0; p < na; ++p) {
+        const int i = g->h_order[p];
         for (int j = 0; j < d->n_det; ++j)
-            rayt[(size_t)i * d->n_det + j] = make_float2((float)(g->h_fp[i].a * (double)j + (g->h_fp[i].c + 1.0)),
+            rayt[(size_t)p * d->n_det + j] = make_float2((float)(g->h_fp[i].a * (double)j + (g->h_fp[i].c + 1.0)),
                                                           (float)g->h_fp[i].b);
+        float idbits;
+        memcpy(&idbits, &i, sizeof(float));
+        angt[p] = make_float2(g->h_fp[i].scale, idbits);
+    }
     cudaError_t ce;
     if ((ce = cudaMalloc(&g->d_rayt, sizeof(float2) * rayt.size())) != cudaSuccess ||
         (ce = cudaMemcpy(g->d_rayt, rayt.data(), sizeof(float2) * rayt.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMalloc(&g->d_angt, sizeof(float2) * na)) != cudaSuccess ||
+        (ce = cudaMemcpy(g->d_angt, angt.data(), sizeof(float2) * na, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_fp, sizeof(FpAngle) * na)) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_bp, sizeof(BpAngle) * na)) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_order, sizeof(int) * na)) != cudaSuccess ||
@@ -162,6 +170,7 @@ extern "C" int scd_geom_destroy(scd_geom_t *g)
     if (g->d_bp) cudaFree(g->d_bp);
     if (g->d_order) cudaFree(g->d_order);
     if (g->d_rayt) cudaFree(g->d_rayt);
+    if (g->d_angt) cudaFree(g->d_angt);
     free(g->h_fp); free(g->h_bp); free(g->h_order);
     free(g);
     return 0;

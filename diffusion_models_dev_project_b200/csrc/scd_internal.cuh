@@ -108,7 +108,9 @@ struct scd_geom {
     FpAngle *d_fp;        // [n_angles]
     BpAngle *d_bp;        // [n_angles]
     int     *d_order;     // [n_angles] angle ids sorted by (class, index)
-    float2  *d_rayt;      // [n_angles][n_det] (u0 + 1, b): start position (row 0) and slope of every ray, from fp64
+    float2  *d_rayt;      // [n_angles][n_det] (u0 + 1, b): start position (row 0) and slope of every ray, from fp64;
+                          // rows in order[] order (position p holds angle order[p])
+    float2  *d_angt;      // [n_angles] (scale, id as int bits) in order[] order
     // host copies
     FpAngle *h_fp;
     BpAngle *h_bp;
