@@ -116,10 +116,14 @@ class B200RayTrafo(BaseRayTrafo):
         the alternative kappa = 1/ds convention.
     """
 
-    def __init__(self, im_shape, num_angles, impl='b200', adjoint_scaling='dphi'):
+    def __init__(self, im_shape, num_angles, impl='b200', adjoint_scaling='dphi', geometry=None):
         if impl not in ('b200', 'odl', 'iradon'):
             raise NotImplementedError(impl)
-        geom = ParallelBeamGeometry2D.from_im_shape(im_shape, num_angles)
+        # `geometry`: an explicit ParallelBeamGeometry2D (arbitrary angle list, detector partition, pixel
+        # size, domain offset) instead of the one SimpleTrafo derives from (im_shape, num_angles)
+        geom = geometry if geometry is not None else ParallelBeamGeometry2D.from_im_shape(im_shape, num_angles)
+        if geometry is not None and (tuple(im_shape) != geom.im_shape or int(num_angles) != geom.n_angles):
+            raise ValueError('geometry does not match im_shape / num_angles')
         super().__init__(im_shape=tuple(int(v) for v in im_shape), obs_shape=geom.obs_shape)
         self.geometry = geom
         if adjoint_scaling == 'dphi':
