@@ -1,5 +1,11 @@
+"""Stream launches (with programmatic dependent launch) vs CUDA-graph replay of one DDS data-consistency step.
+
+    python tools/graph_time.py
+Measured on B200: B=1 146 -> 139 us, B=8 278 -> 267 us, B=32 766 -> 735 us (PDL already hides most of the launch latency).
+"""
 import sys, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import diffusion_models_dev_project_b200 as pkg
 dev = torch.device('cuda')
 for B in (1, 8, 32):
