@@ -425,7 +425,10 @@ def run_b200(args):
                     'algorithmic_bytes_per_launch': BYTES[dom] * B, 'launch_ms': sweep_small[dom]['ms'],
                     'shared_memory_pipe_frac_ncu': pipe,
                     'note': 'A/A* are bound by the shared-memory pipe (8 B per tap pair and sample), not HBM: '
-                            'DESIGN.md section 4; large-batch figures in kernels_b%d' % args.kernel_batch}
+                            'DESIGN.md section 4; large-batch figures in kernels_b%d.  traffic is the DRAM '
+                            'traffic under ncu, which flushes the caches before every launch: it is the packed '
+                            'image (2.06 x the images) that the preceding pack pass leaves in L2 when the '
+                            'kernels run back to back' % args.kernel_batch}
         line = {
             'metric': 'SCD samples/sec at 256^2', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
