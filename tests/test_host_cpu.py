@@ -202,6 +202,24 @@ def test_sampler_with_generic_operator_matches_reference_chain(golden):
     assert rel_l2(recon.numpy(), d['recon']) < 1e-5
 
 
+def test_adaptation_loss_tensor_expression_and_tv():
+    """adaptation_loss on a non-B200 operator evaluates the reference's expression (src/utils/exp_utils.py:256-257);
+    tv_loss matches a direct restatement of src/samplers/adaptation.py:7-11."""
+    rt = O.OracleRayTrafo(O.OracleGeometry((16, 16), 6))
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 1, 16, 16, generator=g, requires_grad=True)
+    y = rt(torch.rand(1, 1, 16, 16, generator=g))
+    loss = pkg.adaptation_loss(x, y, rt, 1e-2)
+    ref = torch.mean((rt(x) - y).pow(2)) + 1e-2 * pkg.tv_loss(x)
+    assert torch.equal(loss, ref)
+    loss.backward()
+    assert torch.isfinite(x.grad).all() and float(x.grad.abs().max()) > 0
+    xn = x.detach().numpy()
+    dh = np.abs(xn[..., :, 1:] - xn[..., :, :-1])[..., :-1, :]
+    dw = np.abs(xn[..., 1:, :] - xn[..., :-1, :])[..., :, :-1]
+    assert abs(float(pkg.tv_loss(x)) - float((dh + dw).sum())) < 1e-4
+
+
 def test_metrics_psnr_ssim():
     rng = np.random.default_rng(0)
     gt = rng.random((64, 48))
