@@ -171,6 +171,16 @@ class B200RayTrafo(BaseRayTrafo):
             raise TypeError('%s: float32 required, got %s' % (what, t.dtype))
         return t.contiguous()
 
+    _MAX_CACHED_BUFFERS = 24
+
+    def _cache_put(self, key, buf: Tensor) -> None:
+        """Scratch buffers are cached per (kind, device, batch size); bound the cache so that a caller
+        sweeping over batch sizes does not accumulate device memory (oldest entries go first; the caching
+        allocator keeps their reuse stream-ordered)."""
+        while len(self._work) >= self._MAX_CACHED_BUFFERS:
+            self._work.pop(next(iter(self._work)))
+        self._work[key] = buf
+
     def workspace(self, batch: int, device: torch.device) -> Tensor:
         """Scratch for scd_cg / scd_dds_step (cached per device and batch)."""
         h = self._handle(device)
@@ -179,7 +189,7 @@ class B200RayTrafo(BaseRayTrafo):
         if w is None:
             nbytes = int(h._lib.scd_cg_workspace_bytes(h.ptr, batch))
             w = torch.empty(nbytes + 256, dtype=torch.uint8, device=h.device)
-            self._work[key] = w
+            self._cache_put(key, w)
         return w
 
     def fp_scratch(self, batch: int, device: torch.device) -> Tensor:
@@ -190,7 +200,7 @@ class B200RayTrafo(BaseRayTrafo):
         if w is None:
             nbytes = int(h._lib.scd_fp_scratch_bytes(h.ptr, batch))
             w = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
-            self._work[key] = w
+            self._cache_put(key, w)
         return w
 
     def bp_scratch(self, batch: int, device: torch.device) -> Tensor:
@@ -201,7 +211,7 @@ class B200RayTrafo(BaseRayTrafo):
         if w is None:
             nbytes = int(h._lib.scd_bp_scratch_bytes(h.ptr, batch))
             w = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
-            self._work[key] = w
+            self._cache_put(key, w)
         return w
 
     @staticmethod
@@ -259,7 +269,7 @@ class B200RayTrafo(BaseRayTrafo):
         buf = self._work.get(key)
         if buf is None:
             buf = torch.empty(int(h._lib.scd_sino_il_buffer_bytes(h.ptr, batch)) + 256, dtype=torch.uint8, device=h.device)
-            self._work[key] = buf
+            self._cache_put(key, buf)
         bp, _ = self._aligned(buf)
         scr = self.fp_scratch(batch, x.device)
         with torch.cuda.device(x.device):
