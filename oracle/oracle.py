@@ -198,9 +198,15 @@ class OracleRayTrafo:
     the 4-D <-> flat adapters of BaseRayTrafo (base_ray_trafo.py:75-81,138-146).
     Batches are handled as matrix columns."""
 
-    def __init__(self, geom: OracleGeometry, matched_adjoint=False):
+    def __init__(self, geom: OracleGeometry, matched_adjoint=False, odl_autograd=False):
         import torch  # noqa: F401
         self.geom = geom
+        # odl_autograd: gradients follow ODL's OperatorFunction [3P] (SURVEY.md 8b / Appendix A) instead
+        # of the exact matrix transposes torch.sparse.mm would give: d<g, A x>/dx = A*(g)/c_w and
+        # d<h, A* y>/dy = c_w A(h) with c_w = dphi*ds/dx^2 -- what the reference's SimpleTrafo does
+        # when its LoRA adaptation differentiates through trafo / trafo_adjoint.
+        self.odl_autograd = bool(odl_autograd)
+        self.c_w = geom.dphi * geom.ds / geom.dx ** 2
         self.im_shape = geom.im_shape
         self.obs_shape = geom.obs_shape
         J = joseph_matrix(geom)
@@ -212,19 +218,56 @@ class OracleRayTrafo:
             self.matrix_adj = _to_torch_coo(bp_matrix(geom))
         self.angles = geom.angles
 
-    def trafo(self, x):
+    def _mm(self, matrix, v, out_shape):
         import torch
-        nb, nc = x.shape[:2]
-        flat = x.reshape(nb * nc, -1).T.contiguous()
-        return torch.sparse.mm(self.matrix, flat).T.reshape(nb, nc, *self.obs_shape)
+        nb, nc = v.shape[:2]
+        flat = v.reshape(nb * nc, -1).T.contiguous()
+        return torch.sparse.mm(matrix, flat).T.reshape(nb, nc, *out_shape)
+
+    def trafo(self, x):
+        if self.odl_autograd:
+            return _paired_functions()[0].apply(x, self)
+        return self._mm(self.matrix, x, self.obs_shape)
 
     def trafo_adjoint(self, y):
-        import torch
-        nb, nc = y.shape[:2]
-        flat = y.reshape(nb * nc, -1).T.contiguous()
-        return torch.sparse.mm(self.matrix_adj, flat).T.reshape(nb, nc, *self.im_shape)
+        if self.odl_autograd:
+            return _paired_functions()[1].apply(y, self)
+        return self._mm(self.matrix_adj, y, self.im_shape)
 
     __call__ = trafo
+
+
+_PAIRED = None
+
+
+def _paired_functions():
+    """(trafo, trafo_adjoint) autograd Functions with ODL's gradient pairing (built lazily: torch)."""
+    global _PAIRED
+    if _PAIRED is None:
+        import torch
+
+        class _Trafo(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, x, rt):
+                ctx.rt = rt
+                return rt._mm(rt.matrix, x.detach(), rt.obs_shape)
+
+            @staticmethod
+            def backward(ctx, g):
+                return _Adjoint.apply(g, ctx.rt) / ctx.rt.c_w, None
+
+        class _Adjoint(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, y, rt):
+                ctx.rt = rt
+                return rt._mm(rt.matrix_adj, y.detach(), rt.im_shape)
+
+            @staticmethod
+            def backward(ctx, g):
+                return _Trafo.apply(g, ctx.rt) * ctx.rt.c_w, None
+
+        _PAIRED = (_Trafo, _Adjoint)
+    return _PAIRED
 
 
 # ----------------------------------------- ports of the reference's torch code ---

@@ -185,11 +185,44 @@ def predictors_fixture():
     np.savez_compressed(os.path.join(OUT, 'predictors_small.npz'), **res)
 
 
+from make_golden_args import adapted_args, adapted_config          # noqa: E402
+
+
+def adapted_fixture():
+    """SCD adapted sampling (BASELINE config 5) through the reference's OWN factory, `_adapt`,
+    `adapted_ddim_sde_predictor` and BaseSampler (src/utils/exp_utils.py:225-295,
+    src/samplers/utils.py:220-336) on a small geometry; the operator is the oracle with ODL's
+    gradient pairing, the score model tests/scorenet.AdaptableScore."""
+    from src.utils.exp_utils import get_standard_adapted_sampler as ref_factory
+    from scorenet import AdaptableScore
+    geom = O.OracleGeometry((48, 48), 12)
+    rt = O.OracleRayTrafo(geom, odl_autograd=True)
+    g = torch.Generator().manual_seed(9)
+    gt = torch.nn.functional.avg_pool2d(torch.rand(2, 1, 48, 48, generator=g), 5, 1, 2)
+    y = rt(gt) + 0.01 * torch.randn(2, 1, *geom.obs_shape, generator=g)
+    res = {'gt': gt.numpy(), 'y': y.numpy(), 'im': np.array([48, 48]), 'num_angles': np.array(12)}
+    for dc in ('cg', 'gd'):
+        score = AdaptableScore(r=2, seed=0)
+        sampler = ref_factory(adapted_args(dc), adapted_config(2), score, RefDDPM(), rt, observation=y, device='cpu')
+        torch.manual_seed(13)
+        recon = sampler.sample(logging=False)
+        res['recon_' + dc] = recon.numpy()
+        for name, prm in score.named_parameters():
+            res['param_%s_%s' % (dc, name)] = prm.detach().numpy()
+        print('adapted', dc, 'recon norm', float(recon.norm()),
+              {n: float(p.detach().norm()) for n, p in score.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, 'adapted_small.npz'), **res)
+
+
 if __name__ == '__main__':
+    if sys.argv[1:] == ['adapted']:        # regenerate only the newest fixture
+        adapted_fixture()
+        sys.exit(0)
     schedule_fixture()
     tweedie_ddim_fixture()
     cg_fixture()
     dds_small_fixture()
     predictors_fixture()
+    adapted_fixture()
     dds_fixture()
     print('golden vectors written to', OUT)

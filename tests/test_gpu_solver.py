@@ -159,6 +159,33 @@ def test_dds_small_chain_matches_reference(golden, monkeypatch):
     assert rel_l2(recon, d['recon']) < 1e-4
 
 
+def test_adapted_sampling_matches_reference_chain(golden, monkeypatch):
+    """BASELINE config 5 (SCD adapted sampling): factory -> `_adapt` (Adam through Tweedie, CG, A, A* and
+    the fused adaptation loss) -> adapted predictor -> sampler on the CUDA kernels, against the outputs
+    of the reference's own get_standard_adapted_sampler / _adapt / adapted_ddim_sde_predictor /
+    BaseSampler (tests/golden/make_golden.py:adapted_fixture; operator = oracle with ODL's gradient
+    pairing).  Checks the reconstruction and the adapted parameters, for dc_type cg and gd."""
+    pkg = _pkg()
+    from make_golden_args import adapted_args, adapted_config
+    from scorenet import AdaptableScore
+    from diffusion_models_dev_project_b200.utils import exp_utils as E
+    _patch_noise_to_cpu_generator(monkeypatch)
+    d = golden('adapted_small.npz')
+    rt = pkg.B200RayTrafo(tuple(int(v) for v in d['im']), int(d['num_angles']))
+    y = torch.from_numpy(d['y']).cuda()
+    for dc in ('cg', 'gd'):
+        score = AdaptableScore(r=2, seed=0).cuda()
+        sampler = E.get_standard_adapted_sampler(adapted_args(dc), adapted_config(2, 'cuda'), score, pkg.DDPM(), rt,
+                                                 observation=y, device='cuda')
+        torch.manual_seed(13)
+        recon = sampler.sample(logging=False).cpu().numpy()
+        assert rel_l2(recon, d['recon_' + dc]) < 1e-4, (dc, rel_l2(recon, d['recon_' + dc]))
+        for name, prm in score.named_parameters():
+            ref = d['param_%s_%s' % (dc, name)]
+            assert np.allclose(prm.detach().cpu().numpy(), ref, atol=2e-5), (dc, name, prm, ref)
+        assert score.adapter.scale == 1.0
+
+
 def test_dds_256_reconstruction_psnr_parity(golden, monkeypatch):
     """BASELINE config 1: 256x256, 60 angles, B=1, 100 DDIM steps, CG(5), gamma 0.01, eta 0.15.
     Gate: PSNR within 0.1 dB of the reference sampler (same seeds)."""

@@ -93,9 +93,9 @@ def test_geometry_object():
 class _CpuTrafo(pkg.BaseRayTrafo):
     """BaseRayTrafo subclass over the oracle matrices: exercises the adapters of the boundary type."""
 
-    def __init__(self, geom):
+    def __init__(self, geom, odl_autograd=False):
         super().__init__(geom.im_shape, geom.obs_shape)
-        self.rt = O.OracleRayTrafo(geom)
+        self.rt = O.OracleRayTrafo(geom, odl_autograd=odl_autograd)
 
     def trafo(self, x):
         return self.rt.trafo(x)
@@ -308,6 +308,30 @@ def test_adapted_predictor_and_adapt_run_with_autograd():
         assert xn.shape == x.shape and torch.isfinite(xn).all() and torch.isfinite(x0).all()
     assert score.l.scale == 1.0
     assert float(pkg.tv_loss(torch.ones(1, 1, 4, 4))) == 0.0
+
+
+def test_adapted_sampling_matches_reference_chain(golden):
+    """BASELINE config 5 (SCD adapted sampling) on a CPU-sized chain: this package's factory, `_adapt`,
+    adapted predictor and sampler against the outputs of the reference's own
+    get_standard_adapted_sampler / _adapt / adapted_ddim_sde_predictor / BaseSampler
+    (tests/golden/make_golden.py:adapted_fixture) -- reconstruction and the adapted parameters."""
+    from make_golden_args import adapted_args, adapted_config
+    from scorenet import AdaptableScore
+    from diffusion_models_dev_project_b200.utils import exp_utils as E
+    d = golden('adapted_small.npz')
+    geom = O.OracleGeometry(tuple(int(v) for v in d['im']), int(d['num_angles']))
+    rt = _CpuTrafo(geom, odl_autograd=True)
+    y = torch.from_numpy(d['y'])
+    for dc in ('cg', 'gd'):
+        score = AdaptableScore(r=2, seed=0)
+        sampler = E.get_standard_adapted_sampler(adapted_args(dc), adapted_config(2, 'cpu'), score, pkg.DDPM(), rt,
+                                                 observation=y, device='cpu')
+        torch.manual_seed(13)
+        recon = sampler.sample(logging=False)
+        assert rel_l2(recon.numpy(), d['recon_' + dc]) < 1e-5, dc
+        for name, prm in score.named_parameters():
+            assert np.allclose(prm.detach().numpy(), d['param_%s_%s' % (dc, name)], atol=2e-6), (dc, name)
+        assert score.adapter.scale == 1.0
 
 
 def test_factories_keep_reference_signatures():
