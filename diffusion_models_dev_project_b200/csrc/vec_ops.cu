@@ -21,6 +21,7 @@
 #include "scd_internal.cuh"
 
 #define VEC_THREADS 256
+#define VEC_U 4          /* float4 per thread and array in flight: the reads of a batch are issued together, then its writes */
 
 int scd_vec_blocks_per_sample(int64_t numel, int batch)
 {
@@ -87,6 +88,26 @@ cg_update_xr_kernel(const float *x_in, float *x, float *__restrict__ r,
     __shared__ float red[VEC_THREADS / 32];
     __shared__ float sc[2];
     const int b = blockIdx.y;
+    int64_t lo, hi;
+    slice_of(numel, lo, hi);
+    const size_t base = (size_t)b * numel;
+    const float4 *xi4 = reinterpret_cast<const float4 *>(x_in + base);
+    float4 *x4 = reinterpret_cast<float4 *>(x + base);
+    float4 *r4 = reinterpret_cast<float4 *>(r + base);
+    const float4 *p4 = reinterpret_cast<const float4 *>(p + base);
+    const float4 *d4 = reinterpret_cast<const float4 *>(d + base);
+    // the first batch of vector loads goes out before the scalar phase (its latency hides theirs)
+    float4 xv[VEC_U], rv[VEC_U], pv[VEC_U], dv[VEC_U];
+    const int64_t i_end = hi >> 2;
+    int64_t i0 = (lo >> 2) + threadIdx.x;
+    auto load_batch = [&](int64_t i) {
+#pragma unroll
+        for (int u = 0; u < VEC_U; ++u) {
+            const int64_t k = i + (int64_t)u * VEC_THREADS;
+            if (k < i_end) { xv[u] = xi4[k]; rv[u] = r4[k]; pv[u] = p4[k]; dv[u] = d4[k]; }
+        }
+    };
+    if (VEC4) load_batch(i0);
     // ||r||^2 and <p,d> from their per-block partials: warp 0 and warp 1 add them concurrently (each in
     // the fixed lane-strided + butterfly order of sum_partials), one barrier for both
     if (threadIdx.x < 64) {
@@ -102,26 +123,27 @@ cg_update_xr_kernel(const float *x_in, float *x, float *__restrict__ r,
     __syncthreads();
     const float rr = sc[0], pd = sc[1];
     const float alpha = __fdiv_rn(rr, pd);      // no guard: same as the reference
-    int64_t lo, hi;
-    slice_of(numel, lo, hi);
-    const size_t base = (size_t)b * numel;
     float acc = 0.f;
     if (VEC4) {
-        const float4 *xi4 = reinterpret_cast<const float4 *>(x_in + base);
-        float4 *x4 = reinterpret_cast<float4 *>(x + base);
-        float4 *r4 = reinterpret_cast<float4 *>(r + base);
-        const float4 *p4 = reinterpret_cast<const float4 *>(p + base);
-        const float4 *d4 = reinterpret_cast<const float4 *>(d + base);
-        for (int64_t i = (lo >> 2) + threadIdx.x; i < (hi >> 2); i += VEC_THREADS) {
-            float4 xv = xi4[i], rv = r4[i];
-            const float4 pv = p4[i], dv = d4[i];
-            xv.x = fmaf(alpha, pv.x, xv.x); xv.y = fmaf(alpha, pv.y, xv.y);
-            xv.z = fmaf(alpha, pv.z, xv.z); xv.w = fmaf(alpha, pv.w, xv.w);
-            rv.x = fmaf(-alpha, dv.x, rv.x); rv.y = fmaf(-alpha, dv.y, rv.y);
-            rv.z = fmaf(-alpha, dv.z, rv.z); rv.w = fmaf(-alpha, dv.w, rv.w);
-            x4[i] = xv; r4[i] = rv;
-            acc = fmaf(rv.x, rv.x, acc); acc = fmaf(rv.y, rv.y, acc);
-            acc = fmaf(rv.z, rv.z, acc); acc = fmaf(rv.w, rv.w, acc);
+        // per thread the elements are visited in the same order as a VEC_THREADS-strided loop, so the
+        // partial sums do not depend on VEC_U
+        for (int64_t i = i0; i < i_end; ) {
+#pragma unroll
+            for (int u = 0; u < VEC_U; ++u) {
+                const int64_t k = i + (int64_t)u * VEC_THREADS;
+                if (k < i_end) {
+                    float4 xo = xv[u], ro = rv[u];
+                    xo.x = fmaf(alpha, pv[u].x, xo.x); xo.y = fmaf(alpha, pv[u].y, xo.y);
+                    xo.z = fmaf(alpha, pv[u].z, xo.z); xo.w = fmaf(alpha, pv[u].w, xo.w);
+                    ro.x = fmaf(-alpha, dv[u].x, ro.x); ro.y = fmaf(-alpha, dv[u].y, ro.y);
+                    ro.z = fmaf(-alpha, dv[u].z, ro.z); ro.w = fmaf(-alpha, dv[u].w, ro.w);
+                    x4[k] = xo; r4[k] = ro;
+                    acc = fmaf(ro.x, ro.x, acc); acc = fmaf(ro.y, ro.y, acc);
+                    acc = fmaf(ro.z, ro.z, acc); acc = fmaf(ro.w, ro.w, acc);
+                }
+            }
+            i += (int64_t)VEC_U * VEC_THREADS;
+            if (i < i_end) load_batch(i);
         }
     } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += VEC_THREADS) {
@@ -154,13 +176,28 @@ tweedie_rhs_kernel(const float *__restrict__ x, const float *__restrict__ s,
     scd_pdl_wait();                               // predecessor complete, its writes visible
     scd_pdl_trigger();
     const int b = blockIdx.y;
+    int64_t lo, hi;
+    slice_of(numel, lo, hi);
+    const size_t base = (size_t)b * numel;
+    const float4 *x4 = reinterpret_cast<const float4 *>(x + base);
+    const float4 *s4 = reinterpret_cast<const float4 *>(s + base);
+    const float4 *a4 = reinterpret_cast<const float4 *>(atb + base);
+    float4 xv[VEC_U], sv[VEC_U], av[VEC_U];
+    const int64_t i_end = hi >> 2;
+    const int64_t i0 = (lo >> 2) + threadIdx.x;
+    auto load_batch = [&](int64_t i) {
+#pragma unroll
+        for (int u = 0; u < VEC_U; ++u) {
+            const int64_t k = i + (int64_t)u * VEC_THREADS;
+            av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < i_end) { xv[u] = x4[k]; sv[u] = s4[k]; if (bvec) av[u] = a4[k]; }
+        }
+    };
+    if (VEC4) load_batch(i0);                     // in flight while the schedule look-up resolves
     const float ab = abar_at(abar, n_table, t[b]);
     const float mean = __fsqrt_rn(ab);                       // bar_a.pow(.5)
     const float stdv = __fsqrt_rn(__fsub_rn(1.0f, ab));      // (1 - bar_a).pow(.5)
     const float div = __fdiv_rn(1.0f, mean);                 // mean.pow(-1)
-    int64_t lo, hi;
-    slice_of(numel, lo, hi);
-    const size_t base = (size_t)b * numel;
 #define TW_ONE(X, S_, A, XH, BV)                                                   \
     {                                                                              \
         const float u__ = __fsub_rn((X), __fmul_rn((S_), stdv));                   \
@@ -168,20 +205,22 @@ tweedie_rhs_kernel(const float *__restrict__ x, const float *__restrict__ s,
         (BV) = __fadd_rn((XH), __fmul_rn(gamma, (A)));                             \
     }
     if (VEC4) {
-        const float4 *x4 = reinterpret_cast<const float4 *>(x + base);
-        const float4 *s4 = reinterpret_cast<const float4 *>(s + base);
-        const float4 *a4 = reinterpret_cast<const float4 *>(atb + base);
         float4 *h4 = reinterpret_cast<float4 *>(xhat0 + base);
         float4 *b4 = bvec ? reinterpret_cast<float4 *>(bvec + base) : nullptr;
-        for (int64_t i = (lo >> 2) + threadIdx.x; i < (hi >> 2); i += VEC_THREADS) {
-            const float4 xv = x4[i], sv = s4[i];
-            float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b4) av = a4[i];
-            float4 hv, bv;
-            TW_ONE(xv.x, sv.x, av.x, hv.x, bv.x) TW_ONE(xv.y, sv.y, av.y, hv.y, bv.y)
-            TW_ONE(xv.z, sv.z, av.z, hv.z, bv.z) TW_ONE(xv.w, sv.w, av.w, hv.w, bv.w)
-            h4[i] = hv;
-            if (b4) b4[i] = bv;
+        for (int64_t i = i0; i < i_end; ) {
+#pragma unroll
+            for (int u = 0; u < VEC_U; ++u) {
+                const int64_t k = i + (int64_t)u * VEC_THREADS;
+                if (k < i_end) {
+                    float4 hv, bv;
+                    TW_ONE(xv[u].x, sv[u].x, av[u].x, hv.x, bv.x) TW_ONE(xv[u].y, sv[u].y, av[u].y, hv.y, bv.y)
+                    TW_ONE(xv[u].z, sv[u].z, av[u].z, hv.z, bv.z) TW_ONE(xv[u].w, sv[u].w, av[u].w, hv.w, bv.w)
+                    h4[k] = hv;
+                    if (b4) b4[k] = bv;
+                }
+            }
+            i += (int64_t)VEC_U * VEC_THREADS;
+            if (i < i_end) load_batch(i);
         }
     } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += VEC_THREADS) {
@@ -205,6 +244,23 @@ ddim_kernel(const float *__restrict__ xhat, const float *__restrict__ s,
     scd_pdl_wait();                               // predecessor complete, its writes visible
     scd_pdl_trigger();
     const int b = blockIdx.y;
+    int64_t lo, hi;
+    slice_of(numel, lo, hi);
+    const size_t base = (size_t)b * numel;
+    const float4 *x4 = reinterpret_cast<const float4 *>(xhat + base);
+    const float4 *s4 = reinterpret_cast<const float4 *>(s + base);
+    const float4 *e4 = reinterpret_cast<const float4 *>(eps + base);
+    float4 xv[VEC_U], sv[VEC_U], ev[VEC_U];
+    const int64_t i_end = hi >> 2;
+    const int64_t i0 = (lo >> 2) + threadIdx.x;
+    auto load_batch = [&](int64_t i) {
+#pragma unroll
+        for (int u = 0; u < VEC_U; ++u) {
+            const int64_t k = i + (int64_t)u * VEC_THREADS;
+            if (k < i_end) { xv[u] = x4[k]; sv[u] = s4[k]; ev[u] = e4[k]; }
+        }
+    };
+    if (VEC4) load_batch(i0);                     // in flight while the coefficients are formed
     // mean_t, mean_tminus1 and tbeta in the reference's operation order
     const float m_t = __fsqrt_rn(abar_at(abar, n_table, t[b]));
     const float m_p = __fsqrt_rn(abar_at(abar, n_table, tp[b]));
@@ -216,22 +272,23 @@ ddim_kernel(const float *__restrict__ xhat, const float *__restrict__ s,
     const float cdet = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, mp2),
                                             __fmul_rn(__fmul_rn(tbeta, tbeta), eta2)));
     const float csto = __fmul_rn(eta, tbeta);
-    int64_t lo, hi;
-    slice_of(numel, lo, hi);
-    const size_t base = (size_t)b * numel;
 #define DD_ONE(XH, S_, E)                                                          \
     __fadd_rn(__fadd_rn(__fmul_rn((XH), m_p), __fmul_rn(cdet, (S_))), __fmul_rn(csto, (E)))
     if (VEC4) {
-        const float4 *x4 = reinterpret_cast<const float4 *>(xhat + base);
-        const float4 *s4 = reinterpret_cast<const float4 *>(s + base);
-        const float4 *e4 = reinterpret_cast<const float4 *>(eps + base);
         float4 *o4 = reinterpret_cast<float4 *>(out + base);
-        for (int64_t i = (lo >> 2) + threadIdx.x; i < (hi >> 2); i += VEC_THREADS) {
-            const float4 xv = x4[i], sv = s4[i], ev = e4[i];
-            float4 ov;
-            ov.x = DD_ONE(xv.x, sv.x, ev.x); ov.y = DD_ONE(xv.y, sv.y, ev.y);
-            ov.z = DD_ONE(xv.z, sv.z, ev.z); ov.w = DD_ONE(xv.w, sv.w, ev.w);
-            o4[i] = ov;
+        for (int64_t i = i0; i < i_end; ) {
+#pragma unroll
+            for (int u = 0; u < VEC_U; ++u) {
+                const int64_t k = i + (int64_t)u * VEC_THREADS;
+                if (k < i_end) {
+                    float4 ov;
+                    ov.x = DD_ONE(xv[u].x, sv[u].x, ev[u].x); ov.y = DD_ONE(xv[u].y, sv[u].y, ev[u].y);
+                    ov.z = DD_ONE(xv[u].z, sv[u].z, ev[u].z); ov.w = DD_ONE(xv[u].w, sv[u].w, ev[u].w);
+                    o4[k] = ov;
+                }
+            }
+            i += (int64_t)VEC_U * VEC_THREADS;
+            if (i < i_end) load_batch(i);
         }
     } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += VEC_THREADS)
