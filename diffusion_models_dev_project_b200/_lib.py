@@ -50,6 +50,12 @@ SIGNATURES = {
     "scd_tv_blocks": (C.c_int, [C.c_int, C.c_int]),
     "scd_tv_loss": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scd_tv_grad": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scd_bp_banded": (C.c_int, [C.c_void_p, _F, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scd_bp_il_banded": (C.c_int, [C.c_void_p, _F, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "scd_band_reduce": (C.c_int, [_F, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_void_p), C.c_int, C.c_int, _F, C.c_float, C.c_float, C.c_void_p]),
     "scd_fp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "scd_bp_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "scd_geom_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

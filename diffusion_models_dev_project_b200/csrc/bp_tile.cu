@@ -297,6 +297,40 @@ bp_tile_kernel(const BqParams P)
     // ---- epilogue: axpy, second output, dot-product partials ---------------
     if (warp == 0 && lane == 0 && P.dbg) scd_stamp(P.dbg, 4);       // warp 0 done marching
     const BpEpilogue &E = P.ep;
+    // banded output: the whole tile lies in band K0 / band_rows (band_rows is a multiple of the tile height)
+    float *band_ptr = nullptr;
+    int band_row0 = 0;
+    if (E.n_bands) {
+        const int band = K0 / E.band_rows;
+        band_row0 = band * E.band_rows;
+#pragma unroll
+        for (int i = 0; i < SCD_MAX_BANDS; ++i) if (i == band) band_ptr = E.band_out[i];
+    }
+    if (band_ptr) {
+        // Banded (peer) output: the tile goes through shared memory so that every warp stores whole
+        // 128-byte runs of one image row -- the stores may cross NVLink, where 32-byte fragments are
+        // expensive.  The ring and the tables are dead once every warp has finished marching.
+        constexpr int TP = 33;                                     // padded row of 32 pixels
+        float *tile = reinterpret_cast<float *>(smem_raw);         // [SB][TH][TP]
+        __syncthreads();
+        if (warp < BQ_NW) {
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int m = 0; m < PPT; ++m)
+                    tile[((lq * V + v) * TH + wy * PPT + m) * TP + wx * RPW + lr] = E.c_acc * acc[m][v];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < SB * TH * 32; idx += BQ_THREADS) {
+            const int x = idx & 31, sr = idx >> 5;
+            const int row = sr % TH, sm = sr / TH;
+            const int b = b0 + sm, k0 = K0 + row, kx = K1 + x;
+            if (b < P.batch && k0 < P.n0 && kx < P.n1)
+                band_ptr[((size_t)b * E.band_rows + (k0 - band_row0)) * P.n1 + kx] = tile[sr * TP + x];
+        }
+        scd_stamp(P.dbg, 5);
+        return;
+    }
     float dsum[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) dsum[v] = 0.f;
@@ -409,8 +443,18 @@ static int bq_launch_t(const BqParams &P, const BqConfig &c, cudaStream_t st, in
 int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int batch,
                      int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st)
 {
-    if (!g || !sino_il || !out) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
+    if (!g || !sino_il || (!out && !ep.n_bands)) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
     if (batch <= 0) return 0;
+    if (ep.n_bands) {
+        if (ep.n_bands > SCD_MAX_BANDS || ep.band_rows <= 0 || ep.band_rows % 32 != 0 ||
+            (long)ep.n_bands * ep.band_rows < g->n0) {
+            scd_set_error("scd_bp: bad band layout (%d bands of %d rows for %d image rows; rows must be a multiple of 32)",
+                          ep.n_bands, ep.band_rows, g->n0);
+            return SCD_E_INVALID;
+        }
+        for (int i = 0; i < ep.n_bands; ++i)
+            if (!ep.band_out[i]) { scd_set_error("scd_bp: null band pointer"); return SCD_E_INVALID; }
+    }
     BqConfig c = bq_choose(g, batch, angle_lo, angle_hi);
     if (c.grid.z > 65535) { scd_set_error("scd_bp: batch too large"); return SCD_E_INVALID; }
     if (c.smem > (size_t)g->smem_optin) { scd_set_error("scd_bp: angle table does not fit in shared memory"); return SCD_E_INVALID; }
@@ -421,6 +465,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     P.angle_lo = angle_lo; P.angle_hi = angle_hi; P.SEG = c.SEG; P.AC = c.AC; P.nbuf = c.nbuf;
     P.PADL = g->il_padl; P.NB = g->il_nb; P.group_floats = (size_t)g->n_angles * g->il_nb * c.SB;
     P.ep = ep; P.dbg = scd_debug_stamps();
+    if (ep.n_bands) c.smem = std::max(c.smem, (size_t)c.SB * c.TH * 33 * 4);     // staging tile of the banded epilogue
     const int WY = BQ_NW / c.LPR;
     (void)WY;
 #define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st, g->device);
@@ -451,7 +496,7 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
                   cudaStream_t st)
 {
     if (g && batch == 0) return 0;                 // empty batch: nothing to do (pointers may be null)
-    if (!g || !sino || !out) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
+    if (!g || !sino || (!out && !ep.n_bands)) { scd_set_error("scd_bp: null argument"); return SCD_E_INVALID; }
     if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
         scd_set_error("scd_bp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)",
                       batch, angle_lo, angle_hi, g->n_angles);

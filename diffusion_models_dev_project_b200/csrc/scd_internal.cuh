@@ -154,12 +154,19 @@ size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch);
 //   out  = val; if (out2) out2 = val
 //   if (dot_part): dot_part[b*dot_stride + cta] = sum over the CTA's pixels of
 //        val * (dot_with_add1 ? add1 : val)
+#define SCD_MAX_BANDS 8
 struct BpEpilogue {
     float c_acc;
     const float *add1; float c1;
     const float *add2; float c2;
     float *out2;
     float *dot_part; int dot_stride; int dot_with_add1;
+    // Banded output (angle-sharded multi-GPU backprojection, peer_reduce.cu): when n_bands > 0 the rows
+    // [i*band_rows, (i+1)*band_rows) of every sample are written to band_out[i] -- typically memory of the
+    // GPU that owns band i, mapped into this process -- as a dense [batch][band_rows][n1] array instead
+    // of `out`; band_rows is a multiple of 32 (every tile lies inside one band).
+    float *band_out[SCD_MAX_BANDS] = {};
+    int n_bands = 0, band_rows = 0;
 };
 // sino in user layout; scratch (>= scd_sino_il_bytes) receives the interleaved copy
 int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
@@ -167,6 +174,10 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
                   cudaStream_t st);
 int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int batch,
                      int angle_lo, int angle_hi, const BpEpilogue &ep, cudaStream_t st);
+// banded stores + rank-ordered reduction of the bands (peer_reduce.cu)
+int scd_launch_band_reduce(const float *stage, int n_src, int64_t slot_stride, int batch, int band_rows, int rows,
+                           int n1, int row_lo, int n0, float *const *out_ptrs, int n_out, int multicast,
+                           const float *addend, float c_add, float c_sum, cudaStream_t st);
 int scd_launch_sino_pack(const scd_geom *g, const float *sino, float *sino_il, int batch,
                          int angle_lo, int angle_hi, cudaStream_t st);
 size_t scd_sino_il_bytes(const scd_geom *g, int batch);

@@ -302,6 +302,53 @@ class B200RayTrafo(BaseRayTrafo):
         return self._bp_il(q, v.shape[:-2], gamma * self.adj_scale, addend=v if add_identity else None,
                            addend_scale=1.0 if add_identity else 0.0, angle_range=angle_range)
 
+    # ---------------------------------------- banded (peer-staged) output ----
+    @staticmethod
+    def _ptr_array(ptrs):
+        import ctypes as C
+        return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+    def _bp_banded(self, y: Tensor, scale: float, band_ptrs, band_rows: int, angle_range=None) -> None:
+        """Backprojection whose image rows ``[i*band_rows, (i+1)*band_rows)`` are stored to ``band_ptrs[i]``
+        (device addresses, possibly peer memory) as dense ``[batch][band_rows][n1]`` arrays (scd_bp_banded)."""
+        y = self._prep(y, self.obs_shape, 'trafo_adjoint')
+        h = self._handle(y.device)
+        batch = int(np.prod(y.shape[:-2])) if y.dim() > 2 else 1
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        scr = self.bp_scratch(batch, y.device)
+        with torch.cuda.device(y.device):
+            _lib.check(h._lib.scd_bp_banded(h.ptr, y.data_ptr(), batch, lo, hi, float(scale), self._ptr_array(band_ptrs),
+                                            len(band_ptrs), int(band_rows), scr.data_ptr(), scr.numel(),
+                                            _stream_ptr(y.device)), 'scd_bp_banded')
+
+    def _normal_banded(self, v: Tensor, gamma: float, band_ptrs, band_rows: int, angle_range=None) -> None:
+        """``gamma * A*(A v)`` of this rank's angles with banded output (scd_fp_il + scd_bp_il_banded)."""
+        v = self._prep(v, self.im_shape, 'normal_apply')
+        h = self._handle(v.device)
+        batch = int(np.prod(v.shape[:-2])) if v.dim() > 2 else 1
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        q = self._fp_il(v, angle_range)
+        qp, _ = self._aligned(q)
+        with torch.cuda.device(v.device):
+            _lib.check(h._lib.scd_bp_il_banded(h.ptr, qp, batch, lo, hi, float(gamma * self.adj_scale),
+                                               self._ptr_array(band_ptrs), len(band_ptrs), int(band_rows),
+                                               _stream_ptr(v.device)), 'scd_bp_il_banded')
+
+    def _band_reduce(self, stage_ptr: int, n_src: int, slot_stride: int, batch: int, band_rows: int, rows: int,
+                     row_lo: int, out_ptrs, device, addend: Tensor = None, c_add: float = 0.0, c_sum: float = 1.0,
+                     multicast: bool = False) -> None:
+        """Sum the ``n_src`` staged copies of this rank's band and store it to every ``out_ptrs[p]`` (scd_band_reduce)."""
+        h = self._handle(device)
+        add_ptr = None
+        if addend is not None:
+            addend = self._prep(addend, self.im_shape, 'addend')
+            add_ptr = addend.data_ptr()
+        with torch.cuda.device(device):
+            _lib.check(h._lib.scd_band_reduce(int(stage_ptr), int(n_src), int(slot_stride), int(batch), int(band_rows),
+                                              int(rows), self.im_shape[1], int(row_lo), self.im_shape[0],
+                                              self._ptr_array(out_ptrs), len(out_ptrs), int(bool(multicast)), add_ptr, float(c_add),
+                                              float(c_sum), _stream_ptr(device)), 'scd_band_reduce')
+
     # --------------------------------------------------- reference interface --
     def trafo(self, x: Tensor) -> Tensor:
         if torch.is_grad_enabled() and x.requires_grad:

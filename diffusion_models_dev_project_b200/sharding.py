@@ -13,10 +13,19 @@ Two cases (the reference itself is single-process, single-
   The stack is processed in slice chunks so that the all-reduce of chunk c overlaps the
   backprojection of chunk c+1.  CG vectors are replicated, so every dot product is local.
 
+  With ``reduce='peer'`` (CUDA, one box) the sum rides on the backprojector instead: the image rows are
+  split into one band per rank, the backprojector's epilogue stores every tile straight into the memory
+  of the band's owner (torch symmetric memory: peer buffers mapped into every rank, stores travel over
+  NVLink / NVSwitch while the kernel computes its other tiles), the owner adds the staged copies in rank
+  order and stores the result into every rank's output (``scd_bp_banded`` / ``scd_band_reduce``).  The two
+  cross-GPU ordering points per chunk are stream-ordered NCCL barriers on a side stream.
+
 The wrapped operator only has to provide ``_fp(x, angle_range=)``, ``_bp(y, scale,
 angle_range=)``, ``adj_scale``, ``im_shape`` and ``obs_shape`` -- :class:`B200RayTrafo` does;
 the CPU tests drive the same code with an oracle-backed stand-in over ``gloo``.
 """
+import os
+
 import torch
 import torch.distributed as dist
 from torch import Tensor
@@ -35,11 +44,17 @@ class AngleShardedRayTrafo:
     ``trafo``            -> this rank's rows of ``A x`` (others zero) -- stays sharded.
     ``trafo_adjoint``    -> ``A* y`` summed over ranks (y: full-shape sinogram whose rows outside
                             this rank's range are ignored).
-    ``normal_apply``     -> ``v + gamma * A*(A v)`` with one all-reduce per call.
+    ``normal_apply``     -> ``v + gamma * A*(A v)`` with one all-reduce per call.  With ``reduce='peer'`` the
+                            returned tensor is a view of one of two alternating symmetric buffers: it stays
+                            valid until the second next call (what the CG recurrences need), not longer.
     ``normal_op(gamma)`` -> callable for :func:`..utils.cg.cg` (tensor-op recurrences on replicated vectors).
     """
 
-    def __init__(self, base, group=None, chunk: int = 64):
+    def __init__(self, base, group=None, chunk: int = 64, reduce: str = 'nccl'):
+        if reduce not in ('nccl', 'peer'):
+            raise ValueError("reduce must be 'nccl' or 'peer'")
+        self.reduce = reduce
+        self._peer = None
         self.base = base
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -106,6 +121,13 @@ class AngleShardedRayTrafo:
     def trafo_adjoint(self, y: Tensor) -> Tensor:
         lead = y.shape[:-2]
         yf = y.reshape(-1, 1, *self.obs_shape)
+        if self.reduce == 'peer' and self.world > 1:
+            out = self._peer_state(yf.shape[0], y.device).run(
+                yf.shape[0],
+                lambda lo, hi, ptrs, rows: self.base._bp_banded(yf[lo:hi], self.base.adj_scale, ptrs, rows,
+                                                                angle_range=self.angle_range),
+                None)
+            return out.clone().reshape(*lead, *self.im_shape)     # callers keep A*(y) (rhs of the sampler)
         out = torch.empty(yf.shape[0], 1, *self.im_shape, dtype=y.dtype, device=y.device)
         self._reduce_chunks(
             lambda lo, hi: self.base._bp(yf[lo:hi], self.base.adj_scale, angle_range=self.angle_range),
@@ -115,6 +137,14 @@ class AngleShardedRayTrafo:
     def normal_apply(self, v: Tensor, gamma: float) -> Tensor:
         lead = v.shape[:-2]
         vf = v.reshape(-1, 1, *self.im_shape)
+        if self.reduce == 'peer' and self.world > 1:
+            vf = vf.contiguous()
+            out = self._peer_state(vf.shape[0], v.device).run(
+                vf.shape[0],
+                lambda lo, hi, ptrs, rows: self.base._normal_banded(vf[lo:hi], gamma, ptrs, rows,
+                                                                    angle_range=self.angle_range),
+                vf)                                   # the identity term is added by the owner's reduction
+            return out.reshape(*lead, *self.im_shape)
         out = torch.empty_like(vf)
 
         fused = getattr(self.base, 'normal_apply', None)      # B200RayTrafo: A*A without re-laying-out the sinogram
@@ -129,3 +159,99 @@ class AngleShardedRayTrafo:
 
     def normal_op(self, gamma: float):
         return lambda v: self.normal_apply(v, gamma)
+
+    def _peer_state(self, n_slices: int, device):
+        if self._peer is None or self._peer.capacity < n_slices or self._peer.device != device:
+            self._peer = _PeerReduce(self, n_slices, device)
+        return self._peer
+
+
+def band_layout(n_rows: int, world: int):
+    """Rows per band (a multiple of 32, the tallest backprojector tile) such that ``world`` bands cover
+    ``n_rows`` image rows; band ``r`` = rows ``[r*band_rows, min(n_rows, (r+1)*band_rows))`` (may be empty)."""
+    band_rows = -(-n_rows // world)
+    band_rows = -(-band_rows // 32) * 32
+    return band_rows
+
+
+class _PeerReduce:
+    """Symmetric buffers and the chunk pipeline of ``reduce='peer'`` (see the module docstring).
+
+    ``stage[buf][src rank][chunk slice][band_rows][n1]`` on every rank receives the partial band of every
+    rank; ``result[slice][n0][n1]`` on every rank receives the reduced bands of all owners.  Both live in
+    torch symmetric memory, so every rank holds device addresses of every peer's copy."""
+
+    NBUF = 3        # staging buffers: a rank may run two chunks ahead of the slowest owner
+
+    def __init__(self, sh: 'AngleShardedRayTrafo', capacity: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.sh, self.capacity, self.device = sh, int(capacity), device
+        P, m = sh.world, sh.chunk
+        n0, n1 = sh.im_shape
+        self.band_rows = band_layout(n0, P)
+        self.row_lo = min(n0, sh.rank * self.band_rows)
+        self.rows = max(0, min(n0, (sh.rank + 1) * self.band_rows) - self.row_lo)
+        self.slot = m * self.band_rows * n1                      # floats per (buffer, source rank)
+        group = sh.group if sh.group is not None else dist.group.WORLD
+        self.stage = symm_mem.empty(self.NBUF * P * self.slot, dtype=torch.float32, device=device)
+        self.results = [symm_mem.empty(self.capacity * n0 * n1, dtype=torch.float32, device=device) for _ in range(2)]
+        hs = symm_mem.rendezvous(self.stage, group=group)
+        hr = [symm_mem.rendezvous(r, group=group) for r in self.results]
+        self.stage_ptrs = [int(p) for p in hs.buffer_ptrs]       # base address of every rank's stage / results
+        self.result_ptrs = [[int(p) for p in h.buffer_ptrs] for h in hr]
+        self._handles = (hs, hr)
+        # NVSwitch multicast address of each result buffer (0 when the box has none): the owner's reduction
+        # then stores every value once and the switch replicates it, instead of one store per peer
+        self.result_mc = [int(getattr(h, 'multicast_ptr', 0) or 0) for h in hr]
+        # opt-in (SCD_PEER_MULTICAST=1): measured slower than per-peer stores on 2 GPUs (scalar strong.sys stores),
+        # not yet measured on 8, where it divides the owner's outgoing traffic by the number of GPUs
+        self.use_multicast = all(self.result_mc) and os.environ.get('SCD_PEER_MULTICAST') == '1'
+        self.calls = 0
+        self.flag = torch.zeros(1, device=device)
+        self.comm = torch.cuda.Stream(device=device)
+
+    def _barrier(self):
+        # stream-ordered cross-rank ordering point: completes on this rank only after every rank's
+        # preceding work on its side stream (hence the kernels it waited for) has completed
+        dist.all_reduce(self.flag, op=dist.ReduceOp.SUM, group=self.sh.group)
+
+    def run(self, n: int, produce, addend) -> Tensor:
+        sh = self.sh
+        P, m = sh.world, sh.chunk
+        n0, n1 = sh.im_shape
+        main = torch.cuda.current_stream(self.device)
+        stage_bytes = self.slot * 4
+        which = self.calls % 2
+        self.calls += 1
+        result, result_ptrs, result_mc = self.results[which], self.result_ptrs[which], self.result_mc[which]
+        landed = []                                              # event: barrier after chunk c's stores
+        for c, lo in enumerate(range(0, n, m)):
+            hi = min(n, lo + m)
+            buf = c % self.NBUF
+            if c >= self.NBUF:
+                # the owners have reduced chunk c - NBUF (their reduction precedes their barrier of chunk
+                # c - NBUF + 1 in stream order): its staging buffer may be overwritten
+                main.wait_event(landed[c - self.NBUF + 1])
+            # my partial of band o goes to slot [buf][my rank] of owner o's stage
+            ptrs = [self.stage_ptrs[o] + (buf * P + sh.rank) * stage_bytes for o in range(P)]
+            produce(lo, hi, ptrs, self.band_rows)
+            stored = torch.cuda.Event()
+            stored.record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(stored)
+                self._barrier()                                  # every rank's stores of chunk c have landed
+                ev = torch.cuda.Event()
+                ev.record(self.comm)
+                landed.append(ev)
+                if self.rows > 0:
+                    outs = [result_mc + lo * n0 * n1 * 4] if self.use_multicast else \
+                        [result_ptrs[p] + lo * n0 * n1 * 4 for p in range(P)]
+                    sh.base._band_reduce(self.stage_ptrs[sh.rank] + buf * P * stage_bytes, P, self.slot, hi - lo,
+                                         self.band_rows, self.rows, self.row_lo, outs, self.device,
+                                         addend=None if addend is None else addend[lo:hi],
+                                         c_add=1.0 if addend is not None else 0.0, multicast=self.use_multicast)
+        with torch.cuda.stream(self.comm):
+            self._barrier()                                      # every owner's reduced bands have landed
+        main.wait_stream(self.comm)
+        # the result lives in a symmetric buffer (two alternate: valid until the second next call)
+        return result[:n * n0 * n1].view(n, 1, n0, n1)

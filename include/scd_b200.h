@@ -161,6 +161,35 @@ int scd_tv_blocks(int n0, int n1);
 int scd_tv_loss(const float *x, float *part, int images, int n0, int n1, void *stream);
 int scd_tv_grad(const float *x, float *grad, int images, int n0, int n1, void *stream);
 
+/* Angle-sharded backprojection of one large slice stack over the GPUs of a box (BASELINE.json
+ * config 4; the reference is single-GPU): every GPU backprojects its angle
+ * range and the partial images are summed.  Instead of writing a local partial image and handing
+ * it to a collective, the backprojector can store every tile straight into the memory of the GPU
+ * that owns the tile's band of image rows (peer memory mapped by the caller, e.g. CUDA IPC /
+ * torch symmetric memory), and the owner adds the staged copies:
+ *   scd_bp_banded / scd_bp_il_banded : like scd_bp / scd_bp_il without addend, but rows
+ *       [i*band_rows, (i+1)*band_rows) of every sample go to band_ptrs[i] as a dense
+ *       [batch][band_rows][n1] array (band_ptrs: HOST array of n_bands <= 8 device pointers;
+ *       band_rows a multiple of 32 with n_bands*band_rows >= n0)
+ *   scd_band_reduce : for the `rows` image rows starting at row_lo (the caller's band):
+ *       out_p[sample][row_lo + r][k] = c_sum * sum_{src < n_src} stage[src*slot_stride + dense(sample, r, k)]
+ *                                      + c_add * addend[sample][row_lo + r][k]      (addend may be NULL)
+ *       for every p < n_out (out_ptrs: HOST array of device pointers to [batch][n0][n1] arrays,
+ *       local or peer); the copies are added in src order (deterministic).  With
+ *       out_is_multicast != 0, out_ptrs[0] is ONE NVSwitch multicast address of that array on all
+ *       GPUs (CUDA multicast object / torch symmetric memory `multicast_ptr`): each value is
+ *       stored once with multimem.st and replicated by the switch.
+ * Ordering between GPUs (all stores of a band landed before its reduction; all reductions landed
+ * before the result is read) is the caller's responsibility.                                   */
+int scd_bp_banded(const scd_geom_t *g, const float *sino, int batch, int angle_lo, int angle_hi,
+                  float c_acc, float *const *band_ptrs, int n_bands, int band_rows,
+                  void *scratch, size_t scratch_bytes, void *stream);
+int scd_bp_il_banded(const scd_geom_t *g, const float *sino_il, int batch, int angle_lo, int angle_hi,
+                     float c_acc, float *const *band_ptrs, int n_bands, int band_rows, void *stream);
+int scd_band_reduce(const float *stage, int n_src, int64_t slot_stride_floats, int batch, int band_rows,
+                    int rows, int n1, int row_lo, int n0, float *const *out_ptrs, int n_out,
+                    int out_is_multicast, const float *addend, float c_add, float c_sum, void *stream);
+
 /* Host-buffer variants (pageable or pinned host memory): copy in, run, copy
  * out, synchronise the stream.  These are what a non-PyTorch caller binds.   */
 int scd_fp_host(const scd_geom_t *g, const float *img_host, float *sino_host,

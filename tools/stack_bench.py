@@ -52,6 +52,9 @@ def main():
     ap.add_argument('--chunk', type=int, default=64)
     ap.add_argument('--iters', type=int, default=3)
     ap.add_argument('--check', type=int, default=2, help='slices compared against the un-sharded operator')
+    ap.add_argument('--reduce', default='nccl', choices=['nccl', 'peer'],
+                    help="how the A* partials are summed: chunked NCCL all-reduce, or peer-staged bands written by the "
+                         "backprojector's epilogue (sharding.py)")
     a = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -63,7 +66,7 @@ def main():
     torch.set_grad_enabled(False)
 
     rt = pkg.B200RayTrafo((a.im, a.im), a.angles)
-    sh = AngleShardedRayTrafo(rt, chunk=a.chunk)
+    sh = AngleShardedRayTrafo(rt, chunk=a.chunk, reduce=a.reduce)
     lo, hi = sh.angle_range
     gen = torch.Generator(device=dev).manual_seed(0)          # replicated stack: same seed on every rank
     x = torch.rand(a.slices, 1, a.im, a.im, device=dev, generator=gen)
@@ -88,6 +91,7 @@ def main():
     t_bp_local = timed(lambda: rt._bp(y[:a.chunk], rt.adj_scale, angle_range=(lo, hi)), a.iters, dev, world) \
         * (a.slices / min(a.chunk, a.slices))
     t_bp = timed(lambda: sh.trafo_adjoint(y), a.iters, dev, world)
+    t_normal = timed(lambda: sh.normal_apply(x, 0.01), a.iters, dev, world)
     part = torch.empty(min(a.chunk, a.slices), 1, a.im, a.im, device=dev)
     t_ar = 0.0
     if world > 1:
@@ -100,6 +104,7 @@ def main():
             'workload': 'slice stack %dx%d x %d slices, %d angles x %d bins, angle-sharded over %d GPU(s)'
                         % (a.im, a.im, a.slices, a.angles, n_det, world),
             'n_gpus': world, 'angles_per_rank': nang, 'chunk_slices': a.chunk,
+            'reduce': a.reduce, 'normal_apply_ms': t_normal,
             'A_ms': t_fp, 'Aadj_local_ms': t_bp_local, 'Aadj_with_allreduce_ms': t_bp, 'allreduce_alone_ms': t_ar,
             'overlap_hidden_ms': max(0.0, t_bp_local + t_ar - t_bp),
             'allreduce_bytes': 4 * a.slices * a.im * a.im if world > 1 else 0,
