@@ -50,7 +50,7 @@ class AngleShardedRayTrafo:
     ``normal_op(gamma)`` -> callable for :func:`..utils.cg.cg` (tensor-op recurrences on replicated vectors).
     """
 
-    def __init__(self, base, group=None, chunk: int = 64, reduce: str = 'nccl'):
+    def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl'):
         if reduce not in ('nccl', 'peer'):
             raise ValueError("reduce must be 'nccl' or 'peer'")
         self.reduce = reduce
