@@ -42,6 +42,7 @@ struct BqParams {
     int angle_lo, angle_hi;
     int SEG;                 // bins per staged segment (multiple of 4)
     int AC, nbuf;            // angles per chunk, ring depth
+    int share_taps;          // pair march (3 loads per pixel pair) where |ci| < 1
     int PADL, NB;            // interleaved sinogram row
     size_t group_floats;     // n_angles * NB * SB
     BpEpilogue ep;
@@ -148,6 +149,30 @@ __device__ __forceinline__ void bq_tap(float (&p)[4], float4 l, float4 r, float 
     b = __ffma2_rn(make_float2(l.z, l.w), wl2, b);
     a = __ffma2_rn(make_float2(r.x, r.y), w2, a);
     b = __ffma2_rn(make_float2(r.z, r.w), w2, b);
+    p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+}
+
+// acc += t0*a0 + t1*a1 + t2*a2 (three consecutive bins; one of a0, a2 is zero, see the pair march)
+__device__ __forceinline__ void bq_tap3(float (&p)[1], float t0, float t1, float t2, float a0, float a1, float a2)
+{ p[0] = fmaf(t2, a2, fmaf(t1, a1, fmaf(t0, a0, p[0]))); }
+__device__ __forceinline__ void bq_tap3(float (&p)[2], float2 t0, float2 t1, float2 t2, float a0, float a1, float a2)
+{
+    float2 a = make_float2(p[0], p[1]);
+    a = __ffma2_rn(t0, make_float2(a0, a0), a);
+    a = __ffma2_rn(t1, make_float2(a1, a1), a);
+    a = __ffma2_rn(t2, make_float2(a2, a2), a);
+    p[0] = a.x; p[1] = a.y;
+}
+__device__ __forceinline__ void bq_tap3(float (&p)[4], float4 t0, float4 t1, float4 t2, float a0, float a1, float a2)
+{
+    const float2 w0 = make_float2(a0, a0), w1 = make_float2(a1, a1), w2 = make_float2(a2, a2);
+    float2 a = make_float2(p[0], p[1]), b = make_float2(p[2], p[3]);
+    a = __ffma2_rn(make_float2(t0.x, t0.y), w0, a);
+    b = __ffma2_rn(make_float2(t0.z, t0.w), w0, b);
+    a = __ffma2_rn(make_float2(t1.x, t1.y), w1, a);
+    b = __ffma2_rn(make_float2(t1.z, t1.w), w1, b);
+    a = __ffma2_rn(make_float2(t2.x, t2.y), w2, a);
+    b = __ffma2_rn(make_float2(t2.z, t2.w), w2, b);
     p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
 }
 
@@ -259,6 +284,7 @@ bp_tile_kernel(const BqParams P)
         for (int m = 0; m < PPT; ++m) kyf[m] = (float)(min(k0b + m, P.n0 - 1) - K0);
         const unsigned lane_base = bq_smem_u32(smem_raw) + (unsigned)(lq * V * 4) - (unsigned)BQ_MAGIC_BITS * (unsigned)(SB * 4);
         const unsigned cst_base = bq_smem_u32(cst);
+        const bool share_taps = (PPT % 2 == 0) && P.share_taps;
         int bi = 0; unsigned ph = 0;
         for (int c = 0; c < nchunks; ++c) {
             bq_mbar_wait(&full[bi], ph);
@@ -270,6 +296,31 @@ bp_tile_kernel(const BqParams P)
             for (int i = 0; i < nac; ++i, seg += SEGB, ca += 16u) {
                 const float4 cs = BqVec<4>::ld<0>(ca);
                 const float vb = fmaf(lxf, cs.y, cs.z);
+                if (PPT >= 2 && share_taps && fabsf(cs.x) <= 0.999f) {
+                    // Pair march: the two pixels of a column pair are |ci| < 1 bins apart, so their four
+                    // taps lie in THREE consecutive bins starting at the smaller left index: 3 loads
+                    // instead of 4 (the shared-memory pipe is what bounds this kernel).  Each pixel
+                    // weighs the three bins with (1-w, w, 0) or (0, 1-w, w); the products with an exact
+                    // zero change nothing, the two real taps are added in the same order as in the
+                    // plain march, so the results are bit-identical to it.
+#pragma unroll
+                    for (int m = 0; m + 1 < PPT; m += 2) {
+                        const float z0 = fmaf(kyf[m], cs.x, vb), z1 = fmaf(kyf[m + 1], cs.x, vb);
+                        const float t0 = __fadd_rd(z0, BQ_MAGIC), t1 = __fadd_rd(z1, BQ_MAGIC);
+                        const float w0 = z0 - (t0 - BQ_MAGIC), w1 = z1 - (t1 - BQ_MAGIC);
+                        const int i0 = __float_as_int(t0), i1 = __float_as_int(t1);
+                        const int ib = min(i0, i1);
+                        const unsigned ad = seg + (unsigned)ib * (unsigned)(SB * 4);
+                        const VT b0 = LD::template ld<0>(ad);
+                        const VT b1 = LD::template ld<SB * 4>(ad);
+                        const VT b2 = LD::template ld<2 * SB * 4>(ad);
+                        const bool s0 = i0 != ib, s1 = i1 != ib;          // left tap of the pixel is bin 1
+                        const float u0 = 1.0f - w0, u1 = 1.0f - w1;
+                        bq_tap3(acc[m], b0, b1, b2, s0 ? 0.0f : u0, s0 ? u0 : w0, s0 ? w0 : 0.0f);
+                        bq_tap3(acc[m + 1], b0, b1, b2, s1 ? 0.0f : u1, s1 ? u1 : w1, s1 ? w1 : 0.0f);
+                    }
+                    continue;
+                }
                 float w[PPT];
                 unsigned ad[PPT];
 #pragma unroll
@@ -393,6 +444,10 @@ static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_
     // shorter CTAs hide the staging latency), 16 rows for one lane per pixel
     const int groups = (batch + c.SB - 1) / c.SB;
     int th = c.LPR >= 2 ? 8 : 16;
+    // 16 samples per group: 16-row tiles (two column pairs per thread: 6 tap loads in flight, 3 per pair)
+    // once they still give >= ~3.5 waves of CTAs (measured at 256^2: B = 128: 162 -> 149 us, B = 256:
+    // 310 -> 275 us, B = 64: 89 -> 95 us; 501^2 x 64 slices x 150 angles: 667 -> 579 us)
+    if (c.LPR == 4 && (long)((g->n1 + 31) / 32) * ((g->n0 + 15) / 16) * groups >= 1024) th = 16;
     if (g->tune_bp_tile == 8 || g->tune_bp_tile == 16 || g->tune_bp_tile == 32) th = g->tune_bp_tile;
     if (c.LPR == 4 && th == 32) th = 16;       // 8 pixels x 4 samples per thread would not fit two CTAs per SM
     if (c.LPR == 1 && th == 8) th = 16;        // 16 warps along k0: at least one pixel each
@@ -465,6 +520,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     P.angle_lo = angle_lo; P.angle_hi = angle_hi; P.SEG = c.SEG; P.AC = c.AC; P.nbuf = c.nbuf;
     P.PADL = g->il_padl; P.NB = g->il_nb; P.group_floats = (size_t)g->n_angles * g->il_nb * c.SB;
     P.ep = ep; P.dbg = scd_debug_stamps();
+    P.share_taps = g->tune_bp_share == 1 ? 0 : 1;
     if (ep.n_bands) c.smem = std::max(c.smem, (size_t)c.SB * c.TH * 33 * 4);     // staging tile of the banded epilogue
     const int WY = BQ_NW / c.LPR;
     (void)WY;
