@@ -161,7 +161,7 @@ class AngleShardedRayTrafo:
         return lambda v: self.normal_apply(v, gamma)
 
     def _peer_state(self, n_slices: int, device):
-        if self._peer is None or self._peer.capacity < n_slices or self._peer.device != device:
+        if self._peer is None or self._peer.capacity < n_slices or self._peer.device != device or self._peer.m != self.chunk:
             self._peer = _PeerReduce(self, n_slices, device)
         return self._peer
 
@@ -187,6 +187,7 @@ class _PeerReduce:
         import torch.distributed._symmetric_memory as symm_mem
         self.sh, self.capacity, self.device = sh, int(capacity), device
         P, m = sh.world, sh.chunk
+        self.m = m                                               # the staging slots are sized for this chunk
         n0, n1 = sh.im_shape
         self.band_rows = band_layout(n0, P)
         self.row_lo = min(n0, sh.rank * self.band_rows)
@@ -217,7 +218,7 @@ class _PeerReduce:
 
     def run(self, n: int, produce, addend) -> Tensor:
         sh = self.sh
-        P, m = sh.world, sh.chunk
+        P, m = sh.world, self.m
         n0, n1 = sh.im_shape
         main = torch.cuda.current_stream(self.device)
         stage_bytes = self.slot * 4
