@@ -159,6 +159,29 @@ def test_dds_small_chain_matches_reference(golden, monkeypatch):
     assert rel_l2(recon, d['recon']) < 1e-4
 
 
+def test_cg_gradient_fused_reverse_sweep_equals_autograd():
+    """Differentiating `cg` on the CUDA operator: the hand-written reverse sweep (no autograd graph, A*A through
+    the fused kernels) against autograd through the tensor recurrences with the A / A* autograd Functions."""
+    pkg = _pkg()
+    rt = pkg.B200RayTrafo((64, 64), 16)
+    gamma = 0.05
+    op = rt.normal_op(gamma)
+    generic = lambda v: v + gamma * rt.trafo_adjoint(rt(v))          # noqa: E731  (plain callable: tensor path)
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    for k in (1, 3):
+        x = torch.rand(3, 1, 64, 64, device='cuda', generator=gen, requires_grad=True)
+        b = (torch.rand(3, 1, 64, 64, device='cuda', generator=gen) + 1.0).requires_grad_()
+        w = torch.randn(3, 1, 64, 64, device='cuda', generator=gen)
+        out = pkg.cg(op, x, b, k)
+        assert out.grad_fn is not None and 'CgSelfAdjoint' in type(out.grad_fn).__name__
+        gx, gb = torch.autograd.grad((out * w).sum(), (x, b))
+        ref = pkg.cg(generic, x, b, k)
+        gx_ref, gb_ref = torch.autograd.grad((ref * w).sum(), (x, b))
+        assert rel_l2(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-5
+        assert rel_l2(gx.cpu().numpy(), gx_ref.cpu().numpy()) < 1e-4, k
+        assert rel_l2(gb.cpu().numpy(), gb_ref.cpu().numpy()) < 1e-4, k
+
+
 def test_adapted_sampling_matches_reference_chain(golden, monkeypatch):
     """BASELINE config 5 (SCD adapted sampling): factory -> `_adapt` (Adam through Tweedie, CG, A, A* and
     the fused adaptation loss) -> adapted predictor -> sampler on the CUDA kernels, against the outputs

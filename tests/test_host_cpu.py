@@ -334,6 +334,33 @@ def test_adapted_sampling_matches_reference_chain(golden):
         assert score.adapter.scale == 1.0
 
 
+def test_cg_hand_written_backward_equals_autograd_through_the_recurrences():
+    """The reverse sweep of `_CgSelfAdjointFn` (used for `op = I + gamma A*A` on the CUDA operator, whose
+    gradient is `op` itself) against autograd through the tensor recurrences, in float64 on a symmetric
+    operator built from the oracle's Joseph matrix."""
+    import importlib
+    C = importlib.import_module('diffusion_models_dev_project_b200.utils.cg')
+    geom = O.OracleGeometry((16, 16), 6)
+    J = O.OracleRayTrafo(geom, matched_adjoint=True).matrix.to_dense().double()
+    M = torch.eye(256, dtype=torch.float64) + 0.3 * geom.dphi * geom.ds * (J.T @ J)
+
+    def op(v):
+        return (v.reshape(v.shape[0], -1) @ M.T).reshape(v.shape)
+    gen = torch.Generator().manual_seed(0)
+    for k in (0, 1, 3, 5):
+        x = torch.randn(2, 1, 16, 16, dtype=torch.float64, generator=gen, requires_grad=True)
+        b = torch.randn(2, 1, 16, 16, dtype=torch.float64, generator=gen, requires_grad=True)
+        w = torch.randn(2, 1, 16, 16, dtype=torch.float64, generator=gen)
+        ref = pkg.cg(op, x, b, k)                                  # generic callable: tensor recurrences + autograd
+        gx_ref, gb_ref = torch.autograd.grad((ref * w).sum(), (x, b), allow_unused=True)
+        gb_ref = torch.zeros_like(b) if gb_ref is None else gb_ref
+        out = C._CgSelfAdjointFn.apply(x, b, lambda v: op(v).detach(), k)
+        gx, gb = torch.autograd.grad((out * w).sum(), (x, b))
+        assert torch.equal(out, ref)
+        assert float((gx - gx_ref).norm() / gx_ref.norm()) < 1e-12, k
+        assert float((gb - gb_ref).norm()) <= 1e-12 * max(1.0, float(gb_ref.norm())), k
+
+
 def test_factories_keep_reference_signatures():
     import inspect
     from diffusion_models_dev_project_b200.utils import exp_utils as E
