@@ -92,3 +92,16 @@ def test_angle_and_sample_sharding_world2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert sorted(os.listdir(tmp_path)) == ['ok0', 'ok1']
+
+
+def test_band_layout_covers_the_image_with_tile_aligned_bands():
+    """Row bands of the peer-staged reduction: one band per rank, a multiple of 32 rows (the tallest
+    backprojector tile), together covering the image; trailing bands may be empty."""
+    from diffusion_models_dev_project_b200.sharding import band_layout
+    for n_rows in (16, 33, 64, 256, 501, 1024):
+        for world in (1, 2, 3, 4, 8):
+            rows = band_layout(n_rows, world)
+            assert rows % 32 == 0 and rows * world >= n_rows
+            assert rows - 32 < -(-n_rows // world) <= rows          # no more padding than one tile row
+            covered = sum(max(0, min(n_rows, (r + 1) * rows) - min(n_rows, r * rows)) for r in range(world))
+            assert covered == n_rows
