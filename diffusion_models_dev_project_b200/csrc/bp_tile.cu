@@ -43,6 +43,7 @@ struct BqParams {
     int SEG;                 // bins per staged segment (multiple of 4)
     int AC, nbuf;            // angles per chunk, ring depth
     int share_taps;          // pair march (3 loads per pixel pair) where |ci| < 1
+    int th_eff;              // rows of the tile in use (<= TH): balances single-wave launches over the SMs
     int PADL, NB;            // interleaved sinogram row
     size_t group_floats;     // n_angles * NB * SB
     BpEpilogue ep;
@@ -190,7 +191,7 @@ bp_tile_kernel(const BqParams P)
     constexpr int TH = WY * PPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int K0 = blockIdx.y * TH, K1 = blockIdx.x * 32;
+    const int K0 = blockIdx.y * P.th_eff, K1 = blockIdx.x * 32;
     const int grp = blockIdx.z, b0 = grp * SB;
     const int nang = P.angle_hi - P.angle_lo;
     const int AC = P.AC, NBUF = P.nbuf;
@@ -250,7 +251,7 @@ bp_tile_kernel(const BqParams P)
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const int b = b0 + lq * V + v, k0 = k0b + m;
-                const bool live = b < P.batch && k0 < P.n0 && k1 < P.n1;
+                const bool live = b < P.batch && k0 < P.n0 && k1 < P.n1 && wy * PPT + m < P.th_eff;
                 const size_t o = live ? ((size_t)b * P.n0 + k0) * P.n1 + k1 : 0;
                 pa1[PREF ? m : 0][v] = (live && P.ep.add1) ? P.ep.add1[o] : 0.f;
                 pa2[PREF ? m : 0][v] = (live && P.ep.add2) ? P.ep.add2[o] : 0.f;
@@ -285,11 +286,12 @@ bp_tile_kernel(const BqParams P)
         const unsigned lane_base = bq_smem_u32(smem_raw) + (unsigned)(lq * V * 4) - (unsigned)BQ_MAGIC_BITS * (unsigned)(SB * 4);
         const unsigned cst_base = bq_smem_u32(cst);
         const bool share_taps = (PPT % 2 == 0) && P.share_taps;
+        const bool warp_rows_in_use = wy * PPT < P.th_eff;
         int bi = 0; unsigned ph = 0;
         for (int c = 0; c < nchunks; ++c) {
             bq_mbar_wait(&full[bi], ph);
             if (c == 0) scd_stamp(P.dbg, 3);      // first angle chunk landed (warp 0)
-            const int nac = min(AC, nang - c * AC);
+            const int nac = warp_rows_in_use ? min(AC, nang - c * AC) : 0;     // idle warps only keep the ring moving
             unsigned seg = lane_base + (unsigned)(bi * AC) * SEGB;
             unsigned ca = cst_base + (unsigned)(c * AC) * 16u;
 #pragma unroll 2
@@ -376,7 +378,7 @@ bp_tile_kernel(const BqParams P)
             const int x = idx & 31, sr = idx >> 5;
             const int row = sr % TH, sm = sr / TH;
             const int b = b0 + sm, k0 = K0 + row, kx = K1 + x;
-            if (b < P.batch && k0 < P.n0 && kx < P.n1)
+            if (b < P.batch && k0 < P.n0 && kx < P.n1 && row < P.th_eff)
                 band_ptr[((size_t)b * E.band_rows + (k0 - band_row0)) * P.n1 + kx] = tile[sr * TP + x];
         }
         scd_stamp(P.dbg, 5);
@@ -393,7 +395,7 @@ bp_tile_kernel(const BqParams P)
 #pragma unroll
             for (int m = 0; m < PPT; ++m) {
                 const int k0 = k0b + m;
-                if (k0 < P.n0) {
+                if (k0 < P.n0 && wy * PPT + m < P.th_eff) {
                     const size_t o = ((size_t)b * P.n0 + k0) * P.n1 + k1;
                     float val = E.c_acc * acc[m][v];
                     float a1 = 0.f;
@@ -431,7 +433,7 @@ bp_tile_kernel(const BqParams P)
 }
 
 // ------------------------------------------------------------- host side ---
-struct BqConfig { int V, LPR, SB, PPT, TH, SEG, AC, nbuf; size_t smem; dim3 grid; };
+struct BqConfig { int V, LPR, SB, PPT, TH, th_eff, SEG, AC, nbuf; size_t smem; dim3 grid; };
 
 static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_hi)
 {
@@ -465,7 +467,23 @@ static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_
     c.nbuf = (int)std::max<size_t>(2, std::min<size_t>(BQ_MAX_NBUF, (90 * 1024) / (c.AC * segb)));
     c.nbuf = std::max(1, std::min(c.nbuf, nchunks));
     c.smem = (size_t)c.nbuf * c.AC * segb + 2 * BQ_MAX_NBUF * 8 + (size_t)nang * 16 + (size_t)BQ_NW * c.SB * 4 + 64;
-    c.grid = dim3((g->n1 + 31) / 32, (g->n0 + th - 1) / th, groups);
+    // Rows of the tile in use.  When the whole launch is a single wave of co-resident CTAs (two per SM) the
+    // span is set by the SMs that host the most CTAs: with one pixel per thread, use fewer rows per tile
+    // if that levels the load (256^2, B = 8: 256 tiles of 8 rows = two CTAs on 108 SMs and one on 40 ->
+    // 296 tiles of 7 rows = two on every SM); the unused warps of a tile only keep the ring moving.
+    c.th_eff = th;
+    const long gx = (g->n1 + 31) / 32, slots = 2L * g->sm_count;
+    if (c.PPT == 1 && g->tune_bp_rows != 1 && gx * ((g->n0 + th - 1) / th) * groups <= slots) {
+        long best = ((gx * ((g->n0 + th - 1) / th) * groups + g->sm_count - 1) / g->sm_count) * th;
+        for (int t = th - 1; t >= std::max(4, th / 2); --t) {
+            const long tiles = gx * ((g->n0 + t - 1) / t) * groups;
+            if (tiles > slots) break;
+            const long cost = ((tiles + g->sm_count - 1) / g->sm_count) * t;
+            if (cost < best) { best = cost; c.th_eff = t; }
+        }
+    }
+    if (g->tune_bp_rows > 1 && g->tune_bp_rows <= th && c.PPT == 1) c.th_eff = g->tune_bp_rows;
+    c.grid = dim3((g->n1 + 31) / 32, (g->n0 + c.th_eff - 1) / c.th_eff, groups);
     return c;
 }
 
@@ -511,6 +529,10 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
             if (!ep.band_out[i]) { scd_set_error("scd_bp: null band pointer"); return SCD_E_INVALID; }
     }
     BqConfig c = bq_choose(g, batch, angle_lo, angle_hi);
+    if (ep.n_bands && c.th_eff != c.TH) {          // bands are aligned to whole tiles
+        c.th_eff = c.TH;
+        c.grid.y = (g->n0 + c.TH - 1) / c.TH;
+    }
     if (c.grid.z > 65535) { scd_set_error("scd_bp: batch too large"); return SCD_E_INVALID; }
     if (c.smem > (size_t)g->smem_optin) { scd_set_error("scd_bp: angle table does not fit in shared memory"); return SCD_E_INVALID; }
     BqParams P;
@@ -521,6 +543,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     P.PADL = g->il_padl; P.NB = g->il_nb; P.group_floats = (size_t)g->n_angles * g->il_nb * c.SB;
     P.ep = ep; P.dbg = scd_debug_stamps();
     P.share_taps = g->tune_bp_share == 1 ? 0 : 1;
+    P.th_eff = c.th_eff;
     if (ep.n_bands) c.smem = std::max(c.smem, (size_t)c.SB * c.TH * 33 * 4);     // staging tile of the banded epilogue
     const int WY = BQ_NW / c.LPR;
     (void)WY;
@@ -573,7 +596,7 @@ int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,
 
 int scd_bp_ctas_per_sample_max(const scd_geom *g, int batch)
 {
-    // workspace sizing: independent of the tuning knobs (smallest tile = 32 x 8 pixels)
+    // workspace sizing: independent of the tuning knobs (smallest tile in use = 32 x 4 pixels)
     (void)batch;
-    return ((g->n1 + 31) / 32) * ((g->n0 + 7) / 8);
+    return ((g->n1 + 31) / 32) * ((g->n0 + 3) / 4);
 }

@@ -200,6 +200,7 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_skip_pack")) g->tune_fp_skip_pack = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
     else if (!strcmp(key, "bp_share")) g->tune_bp_share = value;
+    else if (!strcmp(key, "bp_rows")) g->tune_bp_rows = value;
     else { scd_set_error("scd_set_tuning: unknown key '%s'", key); return SCD_E_INVALID; }
     return 0;
 }

@@ -118,7 +118,7 @@ struct scd_geom {
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
     int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan, tune_fp_skip_pack;
-    int tune_bp_tile, tune_bp_share;
+    int tune_bp_tile, tune_bp_share, tune_bp_rows;
     // sample-interleaved sinogram rows (bp_tile.cu): il_padl zero bins, n_det bins, zero bins up to il_nb
     int il_padl, il_nb;
 };

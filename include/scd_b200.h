@@ -207,7 +207,8 @@ void    scd_launch_count_reset(void);
 /* Override launch heuristics (tuning / tests).  key is one of
  * "fp_samples" (samples interleaved per pixel/bin: 1,2,4,8,16), "fp_angles", "fp_rows",
  * "fp_threads", "fp_nbuf", "fp_cluster", "fp_plan", "fp_skip_pack", "bp_tile", "bp_share" (1 = plain
- * march, no tap sharing between the pixels of a column pair); value 0
+ * march, no tap sharing between the pixels of a column pair), "bp_rows" (rows in use per tile; 1 = always the
+ * full tile); value 0
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */
 int scd_set_tuning(scd_geom_t *g, const char *key, int value);
 
