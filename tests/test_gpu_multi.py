@@ -55,12 +55,14 @@ def _worker(rank, world, port, tmp):
         shp = AngleShardedRayTrafo(rt, chunk=3, reduce='peer')
         zp = shp.trafo_adjoint(y)
         assert float((zp - zf).norm() / zf.norm()) < 1e-5
-        assert float((zp - z).norm() / z.norm()) < 1e-6           # same partials, rank-ordered sum
+        # the banded launch keeps whole 16-row tiles (bands are tile-aligned) while the plain launch levels the
+        # SMs with fewer rows per tile: the tap positions are rounded relative to different tile origins
+        assert float((zp - z).norm() / z.norm()) < 1e-5, float((zp - z).norm() / z.norm())
         zp2 = shp.trafo_adjoint(y)
         assert torch.equal(zp, zp2)                                # deterministic
         na = shp.normal_apply(x, gamma)
         nb = sh.normal_apply(x, gamma)
-        assert float((na - nb).norm() / nb.norm()) < 1e-6
+        assert float((na - nb).norm() / nb.norm()) < 1e-5, float((na - nb).norm() / nb.norm())
         solp = pkg.cg(op=shp.normal_op(gamma), x=x, rhs=x + 1.0, n_iter=3)
         assert float((solp - ref).norm() / ref.norm()) < 1e-4
         gathered = [torch.empty_like(solp) for _ in range(world)]
@@ -71,7 +73,7 @@ def _worker(rank, world, port, tmp):
         sh2n, sh2p = AngleShardedRayTrafo(rt2, chunk=2), AngleShardedRayTrafo(rt2, chunk=2, reduce='peer')
         y2 = torch.randn(9, 1, *rt2.obs_shape, device=dev, generator=gen)
         a2, b2 = sh2n.trafo_adjoint(y2), sh2p.trafo_adjoint(y2)
-        assert float((a2 - b2).norm() / a2.norm()) < 1e-6
+        assert float((a2 - b2).norm() / a2.norm()) < 1e-5, float((a2 - b2).norm() / a2.norm())
         # sample sharding: each rank steps its own shard, no collective; shards equal the 1-GPU result
         sde = pkg.DDPM()
         abar = sde.alpha_bar_table(dev)
