@@ -54,6 +54,10 @@ def parse():
     ap.add_argument('--unet', default='aapm', choices=['aapm', 'small'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--kernel-batch', type=int, default=256, help='batch of the large-batch kernel sweep')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='skip the config 3 / 4 / 5 blocks (stack_501, hot_path_sweep, adapted)')
+    ap.add_argument('--cpu-threads', type=int, default=0,
+                    help='host threads of the CPU reference arm (0 = every core this process may use)')
     return ap.parse_args()
 
 
@@ -144,6 +148,28 @@ def make_unet(kind):
     return (aapm_unet() if kind == 'aapm' else small_unet()).eval()
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def build_id():
+    """sha256 (16 hex digits) of the native library the bench loaded and of the sources it was built from, so that a
+    stale .so cannot be benchmarked unnoticed."""
+    import hashlib
+    from diffusion_models_dev_project_b200 import _lib, build as b
+    h = hashlib.sha256()
+    with open(_lib.LIB_PATH, 'rb') as f:
+        h.update(f.read())
+    hs = hashlib.sha256()
+    for src in [os.path.join(b.CSRC, n) for n in b.SOURCES] + list(b.HEADERS):
+        with open(src, 'rb') as f:
+            hs.update(f.read())
+    return {'lib_sha16': h.hexdigest()[:16], 'src_sha16': hs.hexdigest()[:16], 'stale': bool(b.needs_build())}
+
+
 # ------------------------------------------------------------------ CPU arm ---
 def cpu_reference_arm(args, steps, warmup, quiet=False):
     """The reference's CPU path for one reverse step at batch 1 (its MatmulRayTrafo handles one
@@ -154,6 +180,10 @@ def cpu_reference_arm(args, steps, warmup, quiet=False):
     from oracle import ref_harness
     from bench_support.phantoms import disk_ellipses
     torch.set_grad_enabled(False)
+    # torch.distributed.run exports OMP_NUM_THREADS=1: pin the thread count explicitly so that the CPU arm
+    # means the same thing at every N (only rank 0 runs it, so it may use every core of the box)
+    cores = args.cpu_threads if args.cpu_threads > 0 else host_cores()
+    torch.set_num_threads(cores)
     cores = torch.get_num_threads()
     geom = O.OracleGeometry((IM, IM), ANGLES)
     ort = O.OracleRayTrafo(geom)
@@ -190,11 +220,18 @@ def cpu_reference_arm(args, steps, warmup, quiet=False):
     # projector alone, for the per-operator comparison
     ta = time.perf_counter(); ort(x); ta = time.perf_counter() - ta
     tb = time.perf_counter(); ort.trafo_adjoint(y); tb = time.perf_counter() - tb
+    # data-consistency part alone (no score model): Tweedie + CG(5) + DDIM on the host
+    zero_score = lambda x, t: torch.zeros_like(x)                                      # noqa: E731
+    abar_p = O.ref_port_alpha_bar()
+    dc = time.perf_counter()
+    O.ref_port_dds_step(zero_score, x, atb, abar_p, torch.ones(1) * 500., torch.ones(1) * 490., GAMMA, ETA, CG_ITER, ort)
+    dc = time.perf_counter() - dc
     return {'value': 1.0 / (REVERSE_STEPS * dt), 'unit': 'samples/s', 'cores': cores, 'kind': kind,
             'sample': '%d reverse step(s) at batch 1 (of %d per sample): %s UNet + 6 A + 6 A* (torch.sparse.mm) + '
                       'CG/DDIM on host; %.2f s/step; A %.3f s, A* %.3f s per apply'
                       % (steps, REVERSE_STEPS, args.unet, dt, ta, tb),
-            'seconds_per_step': dt, 'fp_seconds': ta, 'bp_seconds': tb}
+            'seconds_per_step': dt, 'fp_seconds': ta, 'bp_seconds': tb,
+            'dc_seconds': dc}
 
 
 def run_reference(args):
@@ -212,6 +249,12 @@ def run_reference(args):
         'cpu_baseline': {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
         'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'host': {'cores_used': cb['cores'], 'cores_available': host_cores(),
+                 'omp_num_threads_env': os.environ.get('OMP_NUM_THREADS')},
+        'data_consistency_only': {'seconds_per_step_batch1': cb['dc_seconds'],
+                                  'samples_per_s': 1.0 / (REVERSE_STEPS * cb['dc_seconds']),
+                                  'note': 'Tweedie + CG(5) (6 A + 6 A*) + DDIM on the host, no score model: the part '
+                                          'this repository replaces'},
     }
     print(json.dumps(line))
 
@@ -404,6 +447,17 @@ def run_b200(args):
     dc_bytes = (CG_ITER + 1) * (BYTES['fp_march'] + BYTES['bp_tile_axpy_dot']) + CG_ITER * BYTES['cg_update_xr'] \
         + (CG_ITER - 1) * BYTES['cg_direction_update'] + BYTES['tweedie_rhs'] + BYTES['ddim']
 
+    # ---- the other BASELINE configurations (all ranks take part: config 4 has a collective) ----
+    extra = {}
+    if not args.no_extra:
+        from bench_support import config_blocks as CB
+        score = None
+        torch.cuda.empty_cache()
+        extra['hot_path_sweep'] = CB.sweep_block(dev, world, rank)
+        extra['stack_501'] = CB.stack_block(dev, world, rank)
+        extra['adapted'] = CB.adapted_block(dev, world, rank)
+        score = None
+
     line = None
     if rank == 0:
         sweep_small = kernel_sweep(rt, B, dev, hbm_peak)
@@ -443,15 +497,18 @@ def run_b200(args):
                          'frac_hbm': dc_bytes * B / (ms_dc * 1e-3) / 1e9 / hbm_peak},
             'kernels_b%d' % B: sweep_small, 'kernels_b%d' % args.kernel_batch: sweep_big,
             'clocks': clk.summary(),
+            'build': build_id(),
         }
+        line.update(extra)
     if world > 1:
         dist.barrier()
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            del score
+            score = None
             torch.cuda.empty_cache()
             cb = cpu_reference_arm(args, steps=2, warmup=1)
             line['cpu_baseline'] = {k: cb[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            line['hot_path']['vs_cpu_data_consistency_only'] = cb['dc_seconds'] / (ms_dc * 1e-3 / B)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -2,13 +2,13 @@
 
 Public surface (names follow the reference's ``src`` package):
 
-    B200RayTrafo / SimpleTrafo, BaseRayTrafo, simulate            (physics)
+    B200RayTrafo / SimpleTrafo, BaseRayTrafo, simulate, SimulatedDataset  (physics)
     cg, DDPM, VESDE, VPSDE, PSNR, SSIM                                  (utils)
     BaseSampler, decomposed_diffusion_sampling_sde_predictor,
     adapted_ddim_sde_predictor, _adapt, ddim, apTweedy, ...       (samplers)
     get_standard_{sde,ray_trafo,sampler,adapted_sampler}          (utils.exp_utils)
 """
-from .physics import BaseRayTrafo, B200RayTrafo, SimpleTrafo, NormalOp, ParallelBeamGeometry2D, simulate
+from .physics import BaseRayTrafo, B200RayTrafo, SimpleTrafo, NormalOp, ParallelBeamGeometry2D, simulate, SimulatedDataset
 from .utils import SDE, VESDE, VPSDE, DDPM, PSNR, SSIM, cg, _EPSILON_PRED_CLASSES, _SCORE_PRED_CLASSES
 from .samplers import (BaseSampler, tv_loss, adaptation_loss, _score_model_adpt, apTweedy, ddim,
                        decomposed_diffusion_sampling_sde_predictor, adapted_ddim_sde_predictor,

@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libscd_b200.so")
+# SCD_B200_LIB selects another build of the same library (the debug build with time stamps, tools/timeline.py)
+LIB_PATH = os.environ.get("SCD_B200_LIB") or os.path.join(_HERE, "_lib", "libscd_b200.so")
 
 SCD_E_INVALID = -10001
 SCD_E_NODEVICE = -10002
@@ -50,6 +51,7 @@ SIGNATURES = {
     "scd_tv_blocks": (C.c_int, [C.c_int, C.c_int]),
     "scd_tv_loss": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scd_tv_grad": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scd_ramp_filter": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_void_p]),
     "scd_bp_banded": (C.c_int, [C.c_void_p, _F, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_bp_il_banded": (C.c_int, [C.c_void_p, _F, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_int, C.c_int,
@@ -63,7 +65,6 @@ SIGNATURES = {
     "scd_launch_count": (C.c_int64, []),
     "scd_launch_count_reset": (None, []),
     "scd_set_tuning": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
-    "scd_debug_set_stamps": (None, [C.c_void_p]),
     "scd_last_error_string": (C.c_char_p, []),
     "scd_version": (C.c_char_p, []),
 }

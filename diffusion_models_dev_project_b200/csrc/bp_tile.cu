@@ -482,7 +482,7 @@ static BqConfig bq_choose(const scd_geom *g, int batch, int angle_lo, int angle_
             if (cost < best) { best = cost; c.th_eff = t; }
         }
     }
-    if (g->tune_bp_rows > 1 && g->tune_bp_rows <= th && c.PPT == 1) c.th_eff = g->tune_bp_rows;
+    if (g->tune_bp_rows >= 4 && g->tune_bp_rows <= th && c.PPT == 1) c.th_eff = g->tune_bp_rows;
     c.grid = dim3((g->n1 + 31) / 32, (g->n0 + c.th_eff - 1) / c.th_eff, groups);
     return c;
 }

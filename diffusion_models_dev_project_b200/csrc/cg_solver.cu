@@ -71,6 +71,10 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     float *rr_a = part, *rr_b = part + (size_t)ps * batch, *pd = part + 2 * (size_t)ps * batch;
     const int nbp = scd_bp_ctas_per_sample(g, batch);
     const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
+    if ((size_t)nbp > L.part_stride || (size_t)nvec > L.part_stride) {
+        scd_set_error("scd_cg: %d partial sums per sample exceed the workspace stride %zu", std::max(nbp, nvec), L.part_stride);
+        return SCD_E_INVALID;
+    }
     const float gs = gamma * (float)g->adj_scale;
     int rc;
     float *q_user = nullptr, *q_il = q;            // q = A p: interleaved layout only

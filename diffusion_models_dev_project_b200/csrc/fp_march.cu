@@ -825,10 +825,10 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
 
     // the plan depends only on the geometry, the configuration and the angle range: keep the last one
     // (the search simulates a few hundred schedules, too slow to repeat at every launch)
-    struct PlanKey { const scd_geom *g; int lo, hi, groups, NA, CS, plan, sm; };
-    static thread_local PlanKey last_key = {nullptr, 0, 0, 0, 0, 0, 0, 0};
+    struct PlanKey { unsigned long long g; int lo, hi, groups, NA, CS, plan, sm; };
+    static thread_local PlanKey last_key = {0ull, 0, 0, 0, 0, 0, 0, 0};
     static thread_local MqPlan last_plan;
-    const PlanKey key = {g, angle_lo, angle_hi, c.groups, c.NA, c.CS, g->tune_fp_plan, g->sm_count};
+    const PlanKey key = {g->id, angle_lo, angle_hi, c.groups, c.NA, c.CS, g->tune_fp_plan, g->sm_count};
     const bool same = key.g == last_key.g && key.lo == last_key.lo && key.hi == last_key.hi && key.groups == last_key.groups &&
                       key.NA == last_key.NA && key.CS == last_key.CS && key.plan == last_key.plan && key.sm == last_key.sm;
     if (!same) {

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <atomic>
 
 static thread_local char    g_err[512] = "";
 static thread_local int64_t g_launches = 0;
@@ -30,9 +31,11 @@ int scd_cuda_fail(cudaError_t e, const char *what)
 
 void scd_count_launch(int n) { g_launches += n; }
 
+#ifdef SCD_DEBUG_STAMPS
 static unsigned long long *g_stamps = nullptr;
 unsigned long long *scd_debug_stamps() { return g_stamps; }
 extern "C" void scd_debug_set_stamps(void *device_buffer) { g_stamps = (unsigned long long *)device_buffer; }
+#endif
 
 bool scd_pdl_enabled()
 {
@@ -81,6 +84,7 @@ extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
     g->x_min = d->x_min; g->y_min = d->y_min; g->dx = d->dx;
     g->s_min = d->s_min; g->ds = d->ds; g->adj_scale = d->adj_scale;
     g->device = dev;
+    { static std::atomic<unsigned long long> next_id{1}; g->id = next_id.fetch_add(1); }
     g->sm_count = prop.multiProcessorCount;
     g->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
@@ -200,7 +204,11 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_skip_pack")) g->tune_fp_skip_pack = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
     else if (!strcmp(key, "bp_share")) g->tune_bp_share = value;
-    else if (!strcmp(key, "bp_rows")) g->tune_bp_rows = value;
+    else if (!strcmp(key, "bp_rows")) {
+        // tiles of fewer than 4 rows would outgrow the per-CTA partial-sum arrays of the CG workspace
+        if (value != 0 && value != 1 && value < 4) { scd_set_error("scd_set_tuning: bp_rows must be 0, 1 or >= 4"); return SCD_E_INVALID; }
+        g->tune_bp_rows = value;
+    }
     else { scd_set_error("scd_set_tuning: unknown key '%s'", key); return SCD_E_INVALID; }
     return 0;
 }

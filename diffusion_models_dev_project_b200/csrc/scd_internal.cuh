@@ -34,18 +34,28 @@ __device__ __forceinline__ void scd_pdl_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void scd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 #endif
 bool scd_pdl_enabled();
-// optional per-CTA time stamps (tools/timeline.py): device buffer of 8 x int64 per CTA, or NULL
-unsigned long long *scd_debug_stamps();
+// Optional per-CTA time stamps (tools/timeline.py): compiled in only with -DSCD_DEBUG_STAMPS (the debug build
+// `python -m diffusion_models_dev_project_b200.build --debug`, which also exports scd_debug_set_stamps, declared
+// in include/scd_b200_debug.h); the default library carries neither the hook nor the stores.
+#ifdef SCD_DEBUG_STAMPS
+unsigned long long *scd_debug_stamps();      // device buffer of 8 x int64 per CTA, or NULL
+#else
+static inline unsigned long long *scd_debug_stamps() { return nullptr; }
+#endif
 #ifdef __CUDACC__
 __device__ __forceinline__ void scd_stamp(unsigned long long *dbg, int slot)
 {
+#ifdef SCD_DEBUG_STAMPS
     if (dbg && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         dbg[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + slot] = t;
     }
+#else
+    (void)dbg; (void)slot;
+#endif
 }
-#endif      // false when the environment variable SCD_NO_PDL is set (A/B runs)
+#endif
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t scd_launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
@@ -102,6 +112,7 @@ struct scd_geom {
     int n0, n1, n_angles, n_det;
     double x_min, y_min, dx, s_min, ds, adj_scale;
     int device;
+    unsigned long long id;  // unique per scd_geom_create (cache keys must not rely on the address: it can be reused)
     int sm_count;
     int smem_optin;       // max dynamic shared memory per block (opt-in), bytes
     // device tables

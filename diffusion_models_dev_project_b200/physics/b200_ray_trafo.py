@@ -136,7 +136,6 @@ class B200RayTrafo(BaseRayTrafo):
         self._handles = {}
         self._work = {}
         self._hlock = threading.Lock()
-        self._fbp_filter = {}
 
     # ------------------------------------------------------------ plumbing ---
     @property
@@ -237,14 +236,24 @@ class B200RayTrafo(BaseRayTrafo):
                                      scr.data_ptr(), scr.numel(), _stream_ptr(x.device)), 'scd_fp')
         return y
 
+    def _out_image(self, lead, device, out):
+        """The result tensor of a backprojection: a new one, or the caller's (``out=``: a contiguous fp32 tensor
+        of the result's shape, e.g. a slice of a larger stack -- the kernel then writes it in place)."""
+        shape = (*lead, *self.im_shape)
+        if out is None:
+            return torch.empty(shape, dtype=torch.float32, device=device)
+        if tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != device:
+            raise ValueError('out: expected a contiguous float32 tensor of shape %r on %s' % (shape, device))
+        return out
+
     def _bp(self, y: Tensor, scale: float, addend: Tensor = None, addend_scale: float = 0.0,
-            angle_range=None) -> Tensor:
+            angle_range=None, out: Tensor = None) -> Tensor:
         y = self._prep(y, self.obs_shape, 'trafo_adjoint')
         h = self._handle(y.device)
         lead = y.shape[:-2]
         batch = int(np.prod(lead)) if len(lead) else 1
         lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
-        x = torch.empty(*lead, *self.im_shape, dtype=torch.float32, device=y.device)
+        x = self._out_image(lead, y.device, out)
         add_ptr = None
         if addend is not None:
             addend = self._prep(addend, self.im_shape, 'addend')
@@ -278,12 +287,12 @@ class B200RayTrafo(BaseRayTrafo):
         return buf
 
     def _bp_il(self, buf: Tensor, lead, scale: float, addend: Tensor = None, addend_scale: float = 0.0,
-               angle_range=None) -> Tensor:
+               angle_range=None, out: Tensor = None) -> Tensor:
         """Backprojection of a buffer written by :meth:`_fp_il` for the same leading shape."""
         h = self._handle(buf.device)
         batch = int(np.prod(lead)) if len(lead) else 1
         lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
-        x = torch.empty(*lead, *self.im_shape, dtype=torch.float32, device=buf.device)
+        x = self._out_image(tuple(lead), buf.device, out)
         add_ptr = None
         if addend is not None:
             addend = self._prep(addend, self.im_shape, 'addend')
@@ -294,13 +303,15 @@ class B200RayTrafo(BaseRayTrafo):
                                         float(addend_scale), _stream_ptr(buf.device)), 'scd_bp_il')
         return x
 
-    def normal_apply(self, v: Tensor, gamma: float, angle_range=None, add_identity: bool = True) -> Tensor:
+    def normal_apply(self, v: Tensor, gamma: float, angle_range=None, add_identity: bool = True,
+                     out: Tensor = None) -> Tensor:
         """``v + gamma*A*(A v)``: the projector writes the sinogram in the layout the backprojector
-        stages from, the axpy is fused into the backprojector's epilogue (no grad)."""
+        stages from, the axpy is fused into the backprojector's epilogue (no grad).  ``out``: write the
+        result into this tensor (may not alias ``v``)."""
         v = self._prep(v, self.im_shape, 'normal_apply')
         q = self._fp_il(v, angle_range)
         return self._bp_il(q, v.shape[:-2], gamma * self.adj_scale, addend=v if add_identity else None,
-                           addend_scale=1.0 if add_identity else 0.0, angle_range=angle_range)
+                           addend_scale=1.0 if add_identity else 0.0, angle_range=angle_range, out=out)
 
     # ---------------------------------------- banded (peer-staged) output ----
     @staticmethod
@@ -417,25 +428,25 @@ class B200RayTrafo(BaseRayTrafo):
         return x_next, xhat0
 
     # ----------------------------------------------------------------- fbp ---
-    def _ramp(self, device):
-        f = self._fbp_filter.get(device)
-        if f is None:
-            n_det = self.obs_shape[1]
-            n_pad = max(64, 1 << int(np.ceil(np.log2(2 * n_det))))
-            freq = np.fft.rfftfreq(n_pad, d=self.geometry.ds)          # cycles per length unit
-            f = (torch.from_numpy(np.abs(freq)).to(torch.float32).to(device), n_pad)
-            self._fbp_filter[device] = f
-        return f
+    def ramp_filter(self, observation: Tensor) -> Tensor:
+        """Detector-axis ramp filter of :meth:`fbp` (``scd_ramp_filter``: direct convolution with the
+        band-limited ramp of Kak & Slaney in shared memory, divided by the detector cell size)."""
+        y = self._prep(observation, self.obs_shape, 'fbp')
+        h = self._handle(y.device)
+        batch = int(np.prod(y.shape[:-2])) if y.dim() > 2 else 1
+        out = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _lib.check(h._lib.scd_ramp_filter(h.ptr, y.data_ptr(), out.data_ptr(), batch, _stream_ptr(y.device)),
+                       'scd_ramp_filter')
+        return out
 
     def fbp(self, observation: Tensor) -> Tensor:
-        """Ram-Lak filtered back-projection (zero-padded FFT ramp filter, then the
-        pixel-driven backprojector with weight ``dphi``): ``fbp(A x) ~ x``.
-        Counterpart of ``odl.tomo.fbp_op`` used at reference src/physics/trafo.py:34,67;
-        filter recipe as in src/physics/utils.py:11-33."""
-        y = self._prep(observation, self.obs_shape, 'fbp')
-        ramp, n_pad = self._ramp(y.device)
-        spec = torch.fft.rfft(y, n=n_pad, dim=-1)
-        # irfft(rfft(p)*|xi|) is the Riemann sum of (p * h)(s_j) including the ds
-        # factor, so f = int_0^pi (p_theta * h)(x.theta) dtheta ~ dphi * sum_i lerp(...)
-        filt = torch.fft.irfft(spec * ramp, n=n_pad, dim=-1)[..., :self.obs_shape[1]].contiguous()
-        return self._bp(filt, self.geometry.dphi)
+        """Ram-Lak filtered back-projection: ``fbp(A x) ~ x``.
+
+        Counterpart of ``SimpleTrafo.fbp`` (reference src/physics/trafo.py:34,42,67).  The filter is the
+        recipe of the reference's ``filter_sinogram`` (src/physics/utils.py:11-33: rows zero-padded to a power
+        of two >= 2 N_s, "ramp" Fourier filter ``2 Re FFT(f)`` of the Kak-Slaney kernel, scale
+        ``pi/(2 N_theta)``), evaluated as the equivalent linear convolution by ``scd_ramp_filter``; the
+        recipe's constants are split as ``2 * pi/(2 N_theta) = dphi`` (the weight of the pixel-driven
+        backprojector) times ``1/ds`` (the recipe assumes a unit detector cell; ours is ``ds``)."""
+        return self._bp(self.ramp_filter(observation), self.geometry.dphi)

@@ -48,6 +48,8 @@ class AngleShardedRayTrafo:
                             returned tensor is a view of one of two alternating symmetric buffers: it stays
                             valid until the second next call (what the CG recurrences need), not longer.
     ``normal_op(gamma)`` -> callable for :func:`..utils.cg.cg` (tensor-op recurrences on replicated vectors).
+
+    Inference-only: the sharded operators do not record autograd graphs and raise if an input requires grad.
     """
 
     def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl'):
@@ -71,6 +73,7 @@ class AngleShardedRayTrafo:
 
     # ---------------------------------------------------------------- A ----
     def trafo(self, x: Tensor) -> Tensor:
+        self._no_grad_only(x, 'trafo')
         return self.base._fp(x, angle_range=self.angle_range)
 
     __call__ = trafo
@@ -83,42 +86,58 @@ class AngleShardedRayTrafo:
         return y_local
 
     # --------------------------------------------------------------- A* ----
+    @staticmethod
+    def _no_grad_only(t: Tensor, what: str) -> None:
+        """The sharded view is inference-only: its operators bypass the autograd Functions of the wrapped
+        operator (the partial results live in recycled / symmetric buffers autograd could not save), so a
+        gradient through A*A would be dropped silently.  Refuse instead."""
+        if torch.is_grad_enabled() and t.requires_grad:
+            raise RuntimeError('AngleShardedRayTrafo.%s does not support autograd (inference-only view): call it '
+                               'under torch.no_grad() or detach the input' % what)
+
     def _reduce_chunks(self, produce, n: int, out: Tensor) -> Tensor:
-        """``out[c] = all_reduce(produce(c))`` over slice chunks, communication of chunk c
-        overlapping the computation of chunk c+1 (side stream on CUDA)."""
+        """``out[c] = all_reduce(produce(c))`` over slice chunks, communication of chunk c overlapping the
+        computation of chunk c+1 (side stream on CUDA).  ``produce(lo, hi, dst)`` writes this rank's partial of
+        slices ``[lo, hi)`` into ``dst = out[lo:hi]`` (or returns another tensor, which is then copied): the
+        partial is reduced IN PLACE, so the stack is written once and read once by the collective -- no
+        temporary, no copy-out."""
+        def make(lo, hi):
+            dst = out[lo:hi]
+            res = produce(lo, hi, dst)
+            if res is not dst and res.data_ptr() != dst.data_ptr():
+                dst.copy_(res)
+            return dst
         if self.world == 1:
             for lo in range(0, n, self.chunk):
-                out[lo:lo + self.chunk] = produce(lo, min(n, lo + self.chunk))
+                make(lo, min(n, lo + self.chunk))
             return out
         on_cuda = out.is_cuda
         if on_cuda and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=out.device)
         pending = []
         for lo in range(0, n, self.chunk):
-            hi = min(n, lo + self.chunk)
-            part = produce(lo, hi)
+            part = make(lo, min(n, lo + self.chunk))
             if on_cuda:
                 ready = torch.cuda.Event()
                 ready.record(torch.cuda.current_stream(out.device))
                 with torch.cuda.stream(self._comm_stream):
                     self._comm_stream.wait_event(ready)
                     dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
-                    part.record_stream(self._comm_stream)
-                pending.append((lo, hi, part))
             else:
-                work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-                pending.append((lo, hi, part, work))
+                pending.append(dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         if on_cuda:
             torch.cuda.current_stream(out.device).wait_stream(self._comm_stream)
-            for lo, hi, part in pending:
-                out[lo:hi] = part
+            out.record_stream(self._comm_stream)
         else:
-            for lo, hi, part, work in pending:
+            for work in pending:
                 work.wait()
-                out[lo:hi] = part
         return out
 
+    def _base_takes_out(self) -> bool:
+        return getattr(self.base, '_out_image', None) is not None
+
     def trafo_adjoint(self, y: Tensor) -> Tensor:
+        self._no_grad_only(y, 'trafo_adjoint')
         lead = y.shape[:-2]
         yf = y.reshape(-1, 1, *self.obs_shape)
         if self.reduce == 'peer' and self.world > 1:
@@ -129,12 +148,16 @@ class AngleShardedRayTrafo:
                 None)
             return out.clone().reshape(*lead, *self.im_shape)     # callers keep A*(y) (rhs of the sampler)
         out = torch.empty(yf.shape[0], 1, *self.im_shape, dtype=y.dtype, device=y.device)
-        self._reduce_chunks(
-            lambda lo, hi: self.base._bp(yf[lo:hi], self.base.adj_scale, angle_range=self.angle_range),
-            yf.shape[0], out)
+
+        def produce(lo, hi, dst):
+            if self._base_takes_out():
+                return self.base._bp(yf[lo:hi], self.base.adj_scale, angle_range=self.angle_range, out=dst)
+            return self.base._bp(yf[lo:hi], self.base.adj_scale, angle_range=self.angle_range)
+        self._reduce_chunks(produce, yf.shape[0], out)
         return out.reshape(*lead, *self.im_shape)
 
     def normal_apply(self, v: Tensor, gamma: float) -> Tensor:
+        self._no_grad_only(v, 'normal_apply')
         lead = v.shape[:-2]
         vf = v.reshape(-1, 1, *self.im_shape)
         if self.reduce == 'peer' and self.world > 1:
@@ -145,17 +168,18 @@ class AngleShardedRayTrafo:
                                                                     angle_range=self.angle_range),
                 vf)                                   # the identity term is added by the owner's reduction
             return out.reshape(*lead, *self.im_shape)
-        out = torch.empty_like(vf)
-
+        out = torch.empty_like(vf, memory_format=torch.contiguous_format)
         fused = getattr(self.base, 'normal_apply', None)      # B200RayTrafo: A*A without re-laying-out the sinogram
+        first = self.rank == 0        # the identity term of op rides on rank 0's partial: the sum is the result
 
-        def produce(lo, hi):
-            if fused is not None:
-                return fused(vf[lo:hi], gamma, angle_range=self.angle_range, add_identity=False)
+        def produce(lo, hi, dst):
+            if fused is not None and self._base_takes_out():
+                return fused(vf[lo:hi], gamma, angle_range=self.angle_range, add_identity=first, out=dst)
             q = self.base._fp(vf[lo:hi], angle_range=self.angle_range)
-            return self.base._bp(q, gamma * self.base.adj_scale, angle_range=self.angle_range)
+            part = self.base._bp(q, gamma * self.base.adj_scale, angle_range=self.angle_range)
+            return part + vf[lo:hi] if first else part
         self._reduce_chunks(produce, vf.shape[0], out)
-        return (vf + out).reshape(*lead, *self.im_shape)
+        return out.reshape(*lead, *self.im_shape)
 
     def normal_op(self, gamma: float):
         return lambda v: self.normal_apply(v, gamma)

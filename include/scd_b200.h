@@ -161,6 +161,16 @@ int scd_tv_blocks(int n0, int n1);
 int scd_tv_loss(const float *x, float *part, int images, int n0, int n1, void *stream);
 int scd_tv_grad(const float *x, float *grad, int images, int n0, int n1, void *stream);
 
+/* Ramp filter of the filtered back-projection: every sinogram row is convolved along the detector
+ * axis with the band-limited ramp (Kak & Slaney / the "ramp" Fourier filter of the reference's recipe)
+ * and divided by the detector cell size:
+ *   out[b][i][k] = (1/ds) * sum_j sino[b][i][j] * h(|k-j|),  h(0) = 1/4, h(odd n) = -1/(pi n)^2, else 0
+ * so that fbp(y) = scd_bp(scd_ramp_filter(y)) with c_acc = pi/n_angles satisfies fbp(A x) ~ x.
+ * `out` may not alias `sino`.
+ * Replaces: the filtering half of SimpleTrafo.fbp (src/physics/trafo.py:34,42,67); recipe
+ * filter_sinogram (src/physics/utils.py:11-33: zero-padded FFT, ramp, pi/(2 n_angles)).        */
+int scd_ramp_filter(const scd_geom_t *g, const float *sino, float *out, int batch, void *stream);
+
 /* Angle-sharded backprojection of one large slice stack over the GPUs of a box (BASELINE.json
  * config 4; the reference is single-GPU): every GPU backprojects its angle
  * range and the partial images are summed.  Instead of writing a local partial image and handing
@@ -211,10 +221,6 @@ void    scd_launch_count_reset(void);
  * full tile); value 0
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */
 int scd_set_tuning(scd_geom_t *g, const char *key, int value);
-
-/* Profiling aid (tools/timeline.py): when set to a device buffer of 8 x int64 per CTA, fp_march and
- * bp_tile record %globaltimer at their phase boundaries.  NULL (default) disables it.     */
-void scd_debug_set_stamps(void *device_buffer);
 
 const char *scd_last_error_string(void);
 const char *scd_version(void);

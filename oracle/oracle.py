@@ -331,3 +331,43 @@ def ref_port_dds_step(score, x, atb, abar, t, tm1, gamma, eta, n_iter, ray_trafo
         if noise is None:
             noise = torch.randn_like(xhat)
         return ref_port_ddim(s, xhat, abar, t, tm1, eta, noise), xhat0
+
+
+# --------------------------------------------------------------- fbp ---
+def ramp_fourier_filter(size):
+    """The "ramp" Fourier filter torch-radon's ``FourierFilters.get(size, 'ramp')`` returns [3P; it is
+    scikit-image's ``_get_fourier_filter``]: ``2 * Re(FFT(f))`` with ``f`` the band-limited ramp of
+    Kak & Slaney eq. 61 on a circular grid of ``size`` samples -- the filter the reference multiplies with
+    at src/physics/utils.py:25-27."""
+    n = np.concatenate([np.arange(1, size / 2 + 1, 2, dtype=int), np.arange(size / 2 - 1, 0, -2, dtype=int)])
+    f = np.zeros(size)
+    f[0] = 0.25
+    f[1::2] = -1.0 / (np.pi * n) ** 2
+    return 2.0 * np.real(np.fft.fft(f))
+
+
+def filter_sinogram(sino):
+    """Restatement of the reference's ``filter_sinogram`` (src/physics/utils.py:11-33), statement by
+    statement, in float64: pad the detector axis to ``max(64, 2^ceil(log2(2 N_s)))`` (:18-20), FFT (:22),
+    multiply with the ramp filter (:24-26), inverse FFT (:28), drop the padding and scale by
+    ``pi / (2 N_theta)`` (:30)."""
+    sino = np.asarray(sino, dtype=np.float64)
+    size, n_angles = sino.shape[-1], sino.shape[-2]
+    padded_size = max(64, int(2 ** np.ceil(np.log2(2 * size))))
+    pad = padded_size - size
+    padded = np.concatenate([sino, np.zeros(sino.shape[:-1] + (pad,))], axis=-1)
+    spec = np.fft.fft(padded, axis=-1) * ramp_fourier_filter(padded_size)
+    filtered = np.fft.ifft(spec, axis=-1)[..., :-pad] * (np.pi / (2 * n_angles))
+    return filtered.real
+
+
+def fbp(geom: OracleGeometry, sino):
+    """Filtered back-projection as the reference's iradon branch composes it (src/physics/trafo.py:42:
+    ``backprojection(filter_sinogram(x))``): the recipe above followed by the plain pixel-driven sum of
+    interpolated detector values.  The recipe is written for a unit detector cell (torch-radon's
+    ``det_spacing = 1``); on the ODL detector of this geometry (cell ``ds``) the discrete ramp carries
+    ``1/ds^2`` and the Riemann sum ``ds``, so the result is divided by ``ds`` -- the only factor added to the
+    reference recipe, needed for ``fbp(A x) ~ x`` [the ODL branch, ``odl.tomo.fbp_op``, is 3P and unpinned]."""
+    q = filter_sinogram(sino) / geom.ds
+    plain = OracleGeometry(geom.im_shape, geom.n_angles, adj_scale=1.0)
+    return bp(plain, q.astype(np.float32))

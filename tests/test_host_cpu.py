@@ -391,3 +391,115 @@ def test_psnr():
     gt = np.zeros((4, 4)); gt[0, 0] = 1.0
     assert pkg.PSNR(gt, gt) == float('inf')
     assert abs(pkg.PSNR(gt + 0.1, gt) - 20.0) < 1e-9
+
+
+# ------------------------------------------- simulate / data helpers / phantoms / fbp recipe ----
+class _MatrixTrafo:
+    """Generic CPU operator (dense matrices) with the attributes the data helpers touch."""
+
+    def __init__(self, im_shape=(6, 5), obs_shape=(4, 7), seed=0):
+        g = torch.Generator().manual_seed(seed)
+        self.im_shape, self.obs_shape = im_shape, obs_shape
+        self.M = torch.randn(obs_shape[0] * obs_shape[1], im_shape[0] * im_shape[1], generator=g)
+
+    def trafo(self, x):
+        return (x.reshape(*x.shape[:-2], -1) @ self.M.T).reshape(*x.shape[:-2], *self.obs_shape)
+
+    __call__ = trafo
+
+    def fbp(self, y):
+        return (y.reshape(*y.shape[:-2], -1) @ self.M).reshape(*y.shape[:-2], *self.im_shape) * 0.01
+
+
+def test_simulate_reproduces_the_reference_measurements(golden):
+    """`simulate` (reference src/physics/simulation.py:12-23) against the `y_i` the REFERENCE's simulate
+    produced for the config-1 fixture (tests/golden/make_golden.py: oracle operator, default_rng(1 + i)): same
+    random stream, same noise level, no host read-back of the level."""
+    d = golden('dds_256.npz')
+    ort = O.OracleRayTrafo(O.OracleGeometry((256, 256), 60))
+    for i in range(2):
+        gt = torch.from_numpy(d['gt_%d' % i])
+        y = pkg.simulate(gt, ort, 0.01, rng=np.random.default_rng(1 + i))
+        assert y.dtype == torch.float32 and tuple(y.shape) == (1, 1, 60, 365)
+        assert np.array_equal(y.numpy(), d['y_%d' % i]), float(np.abs(y.numpy() - d['y_%d' % i]).max())
+    y2, level = pkg.simulate(gt, ort, 0.01, rng=np.random.default_rng(2), return_noise_level=True)
+    assert np.array_equal(y2.numpy(), d['y_1'])
+    assert abs(level - 0.01 * float(ort(gt).abs().mean())) < 1e-12
+
+
+@pytest.mark.needs_reference
+def test_simulate_and_dataset_equal_the_reference_code():
+    from oracle import ref_harness
+    ref_harness.import_reference()
+    from src.physics.simulation import simulate as ref_simulate, SimulatedDataset as RefDataset
+    rt = _MatrixTrafo()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(3, 1, 6, 5, generator=g)
+    a = ref_simulate(x, rt, 0.05, rng=np.random.default_rng(7))
+    b = pkg.simulate(x, rt, 0.05, rng=np.random.default_rng(7))
+    assert torch.equal(a, b)
+    imgs = [torch.rand(1, 6, 5, generator=g) for _ in range(3)]
+    for k, (ra, rb) in enumerate(zip(RefDataset(imgs, rt, 0.05), pkg.SimulatedDataset(imgs, rt, 0.05))):
+        for u, v in zip(ra, rb):
+            assert torch.equal(u, v), k
+
+
+def test_simulated_dataset_and_get_data_from_ground_truth():
+    rt = _MatrixTrafo()
+    g = torch.Generator().manual_seed(5)
+    imgs = [torch.rand(1, 6, 5, generator=g) for _ in range(4)]
+    ds = pkg.SimulatedDataset(imgs, rt, 0.1, use_fixed_seeds_starting_from=3)
+    assert len(ds) == 4
+    y2, x2, f2 = ds[2]
+    assert tuple(y2.shape) == (1, 4, 7) and tuple(x2.shape) == (1, 6, 5) and tuple(f2.shape) == (1, 6, 5)
+    ref = pkg.simulate(imgs[2][None], rt, 0.1, rng=np.random.default_rng(3 + 2))[0]
+    assert torch.equal(y2, ref) and torch.equal(f2, rt.fbp(ref[None])[0]) and torch.equal(x2, imgs[2])
+    assert all(torch.equal(a[0], b[0]) for a, b in zip(ds, [ds[i] for i in range(4)]))      # __iter__ == __getitem__
+    with pytest.raises(AssertionError):
+        pkg.SimulatedDataset(imgs, rt, 0.1, rng=np.random.default_rng(0))
+    shared = pkg.SimulatedDataset(imgs, rt, 0.1, use_fixed_seeds_starting_from=None, rng=np.random.default_rng(0))
+    assert not torch.equal(shared[0][0], shared[0][0])             # one generator: consecutive draws differ
+    # get_data_from_ground_truth (reference src/utils/exp_utils.py:322-332): 3-D input gains a batch axis
+    gt, obs, fbp = pkg.get_data_from_ground_truth(imgs[0], rt, 0.0)
+    assert tuple(gt.shape) == (1, 1, 6, 5) and tuple(obs.shape) == (1, 1, 4, 7) and tuple(fbp.shape) == (1, 1, 6, 5)
+    assert torch.equal(obs, rt(gt)) and torch.equal(fbp, rt.fbp(obs))
+    gt4, _, _ = pkg.get_data_from_ground_truth(gt, rt, 0.0)
+    assert gt4 is gt
+
+
+def test_disk_ellipse_phantoms_are_deterministic_and_normalised():
+    """Synthetic stand-in of DiskDistributedEllipsesDataset (reference src/dataset/ellipses.py:121-136 random
+    parameters, :72-79 foreground normalisation)."""
+    from bench_support.phantoms import disk_ellipses
+    a = disk_ellipses(3, 64, seed=1)
+    b = disk_ellipses(3, 64, seed=1)
+    c = disk_ellipses(3, 64, seed=2)
+    assert a.shape == (3, 1, 64, 64) and a.dtype == np.float32
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.array_equal(disk_ellipses(2, 64, seed=1), a[:2])            # a prefix of the same stream
+    for img in a[:, 0]:
+        assert img.min() >= 0.0 and abs(img.max() - 1.0) < 1e-6
+        r = np.hypot(*np.meshgrid((np.arange(64) + .5) / 32 - 1, (np.arange(64) + .5) / 32 - 1, indexing='ij'))
+        assert (img != 0).mean() > 0.05 and img[r > 0.95].max() < 0.5     # mass sits in the central disk
+
+
+def test_oracle_fbp_recipe():
+    """oracle.filter_sinogram restates the reference's zero-padded FFT recipe (src/physics/utils.py:11-33); it
+    equals the linear convolution with the Kak-Slaney ramp (what scd_ramp_filter evaluates), and
+    fbp(A x) ~ x."""
+    geom = O.OracleGeometry((64, 64), 90)
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal((2, 90, geom.n_det))
+    q = O.filter_sinogram(y)
+    n = geom.n_det
+    h = np.zeros(n); h[0] = 0.25
+    k = np.arange(1, n, 2); h[k] = -1.0 / (np.pi * k) ** 2
+    H = h[np.abs(np.arange(n)[:, None] - np.arange(n)[None, :])]
+    assert rel_l2(2 * np.pi / (2 * 90) * (y @ H.T), q) < 1e-12
+    assert 0 < O.ramp_fourier_filter(128)[0] < 5e-3 and abs(O.ramp_fourier_filter(128)[64] - 1.0) < 5e-3   # ~2|xi|, small positive DC
+    xx, yy = np.meshgrid(np.arange(64) - 31.5, np.arange(64) - 31.5, indexing='ij')
+    x = ((xx / 20) ** 2 + (yy / 12) ** 2 < 1).astype(np.float32)[None]
+    x = np.asarray(torch.nn.functional.avg_pool2d(torch.from_numpy(x)[None], 5, 1, 2)[0])
+    rec = O.fbp(geom, O.fp(geom, x))
+    assert rel_l2(rec, x) < 0.06
+    assert abs(rec[0, 32, 32] - 1.0) < 0.02

@@ -105,3 +105,19 @@ def test_band_layout_covers_the_image_with_tile_aligned_bands():
             assert rows - 32 < -(-n_rows // world) <= rows          # no more padding than one tile row
             covered = sum(max(0, min(n_rows, (r + 1) * rows) - min(n_rows, r * rows)) for r in range(world))
             assert covered == n_rows
+
+
+def test_sharded_view_refuses_autograd():
+    """The sharded operators bypass the autograd Functions of the wrapped operator: a gradient through A*A would
+    be dropped silently, so inputs that require grad are rejected (single process, world size 1)."""
+    geom = O.OracleGeometry((16, 16), 6)
+    sh = AngleShardedRayTrafo(OracleBase(geom), chunk=2)
+    x = torch.rand(3, 1, 16, 16, requires_grad=True)
+    for call in (lambda: sh(x), lambda: sh.normal_apply(x, 0.1),
+                 lambda: sh.trafo_adjoint(torch.rand(3, 1, *geom.obs_shape, requires_grad=True))):
+        with pytest.raises(RuntimeError, match='does not support autograd'):
+            call()
+    with torch.no_grad():
+        out = sh.normal_apply(x, 0.1)
+    ref = x.detach() + 0.1 * OracleBase(geom)._bp(OracleBase(geom)._fp(x.detach()), geom.adj_scale)
+    assert rel_l2(out.numpy(), ref.numpy()) < 1e-6

@@ -1,5 +1,8 @@
 """Per-CTA phase timeline of fp_march / bp_tile (%globaltimer stamps, scd_debug_set_stamps).
 
+Needs the debug build of the library (compiled with -DSCD_DEBUG_STAMPS; built here if missing -- needs nvcc):
+the default libscd_b200.so carries no stamp code.
+
     python tools/timeline.py --kernel fp --batch 8
 Prints, per phase boundary, min / median / max over the CTAs of the time since the earliest CTA start.
 """
@@ -11,6 +14,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from diffusion_models_dev_project_b200 import build as _build  # noqa: E402
+os.environ['SCD_B200_LIB'] = _build.build(debug=True)
 import diffusion_models_dev_project_b200 as pkg  # noqa: E402
 from diffusion_models_dev_project_b200 import _lib  # noqa: E402
 
@@ -35,6 +40,9 @@ def main():
     if tune:
         rt.set_tuning(dev, **tune)
     lib = _lib.load()
+    import ctypes
+    lib.scd_debug_set_stamps.argtypes = [ctypes.c_void_p]
+    lib.scd_debug_set_stamps.restype = None
     x = torch.rand(a.batch, 1, a.im, a.im, device=dev)
     p = torch.rand_like(x)
     q = rt._fp_il(x)
