@@ -212,7 +212,8 @@ def adapted_block(dev, world, rank, steps=2, warm=1, full_unet=True):
         finite = bool(torch.isfinite(x).all())
         return _max_over_ranks(a.elapsed_time(b) / steps, dev, world), int(lib.scd_launch_count()) // steps, finite
 
-    with torch.enable_grad():
+    import contextlib
+    with torch.enable_grad(), contextlib.redirect_stdout(sys.stderr):        # the factory prints; stdout is the JSON line's
         a2 = copy.copy(args)
         a2.adaptation = 'full'
         path = pkg.get_standard_adapted_sampler(args=a2, config=config, score=AdaptableScore().to(dev), sde=sde,
