@@ -38,7 +38,7 @@ BYTES = {
     'bp_tile': 4 * (IM * IM + ANGLES * NDET),
     'bp_tile_axpy_dot': 4 * (2 * IM * IM + ANGLES * NDET),      # + read of the addend
     'cg_update_xr': 6 * 4 * IM * IM,
-    'cg_direction_update': 3 * 4 * IM * IM,        # p = r + beta p (fused into the pack pass)
+    'cg_direction_update': 3 * 4 * IM * IM,        # p = r + beta p (fused into the backprojector's epilogue)
     'tweedie_rhs': 5 * 4 * IM * IM,
     'ddim': 4 * 4 * IM * IM,
 }
@@ -300,27 +300,30 @@ def kernel_sweep(rt, batch, dev, hbm_peak, iters=20):
     out = {}
     q_il = rt._fp_il(x)                                                    # interleaved sinogram of x (as inside CG)
     lead = x.shape[:-2]
+    x_il = rt._img_il(x)                                                   # sample-interleaved image (as inside CG)
+    p_il = rt._img_il(p)
+    d_il = torch.empty_like(p_il)
     cases = {
-        'fp_packq+fp_march': lambda: rt._fp_il(x),                         # 2 launches: pack pass + march
-        'fp_march': lambda: rt._fp_il(x),                                  # 1 launch (pack skipped, see below)
+        'il_pack+fp_march': lambda: rt._fp_il(x),                          # 2 launches: interleaving pass + march
+        'fp_march': lambda: rt._fp_ilimg(x_il, batch),                     # 1 launch: A of an interleaved image
         'bp_tile': lambda: rt._bp_il(q_il, lead, rt.adj_scale),            # 1 launch
+        'bp_tile_il_axpy': lambda: rt._bp_ilimg(q_il, batch, 0.01 * rt.adj_scale, addend_il=p_il, addend_scale=1.0,
+                                                out_il=d_il),              # 1 launch, interleaved in and out
         'bp_tile_axpy_dot': lambda: rt._bp_il(q_il, lead, 0.01 * rt.adj_scale, addend=p, addend_scale=1.0),
         'A_public': lambda: rt._fp(x),                                     # public trafo: pack + march (user layout out)
         'Aadj_public': lambda: rt._bp(y, rt.adj_scale),                    # public trafo_adjoint: sino_pack + bp_tile
         'tweedie_rhs': lambda: fused.tweedie_rhs(x, s, t, abar, atb=p, gamma=GAMMA),
         'ddim': lambda: fused.ddim_ddpm(x, s, p, t, tp, abar, ETA),
     }
-    BYTES.update({'fp_packq+fp_march': BYTES['fp_march'], 'A_public': BYTES['fp_march'], 'Aadj_public': BYTES['bp_tile']})
+    BYTES.update({'il_pack+fp_march': BYTES['fp_march'], 'A_public': BYTES['fp_march'], 'Aadj_public': BYTES['bp_tile'],
+                  'bp_tile_il_axpy': BYTES['bp_tile_axpy_dot']})
     for name, fn in cases.items():
-        # the march alone: re-use the packed copy left by the previous case (benchmark knob)
-        rt.set_tuning(dev, fp_skip_pack=1 if name == 'fp_march' else 0)
         for _ in range(3):
             fn()
         ms = cuda_time(fn, iters, flush)
-        rt.set_tuning(dev, fp_skip_pack=0)
         gbs = BYTES[name] * batch / (ms * 1e-3) / 1e9
         out[name] = {'ms': ms, 'GB/s': gbs, 'frac_hbm': gbs / hbm_peak}
-    # whole CG solve (6 A + 6 A* + 5 update_xr + 4 update_p)
+    # whole CG solve (6 A + 6 A* + 5 update_xr; direction updates ride on the backprojector's epilogue)
     op = rt.normal_op(GAMMA)
     from diffusion_models_dev_project_b200 import cg
     for _ in range(3):

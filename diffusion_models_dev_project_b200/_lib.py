@@ -40,6 +40,11 @@ SIGNATURES = {
     "scd_sino_il_buffer_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scd_fp_il": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_bp_il": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_float, _F, C.c_float, C.c_void_p]),
+    "scd_img_il_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
+    "scd_img_il_pack": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_void_p]),
+    "scd_img_il_unpack": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_void_p]),
+    "scd_fp_ilimg": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scd_bp_ilimg": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_int, C.c_int, C.c_float, _F, C.c_float, C.c_void_p]),
     "scd_cg_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int]),
     "scd_cg": (C.c_int, [C.c_void_p, _F, _F, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_tweedie_rhs": (C.c_int, [_F, _F, _F, _F, _F, C.c_int, C.c_double, _F, _F, C.c_int, C.c_int64, C.c_void_p]),

@@ -177,8 +177,9 @@ __device__ __forceinline__ void bq_tap3(float (&p)[4], float4 t0, float4 t1, flo
     p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
 }
 
-// V samples per lane, LPR lanes per pixel (SB = V*LPR), PPT pixels per thread
-template <int V, int LPR, int PPT>
+// V samples per lane, LPR lanes per pixel (SB = V*LPR), PPT pixels per thread; IL: the epilogue's images are
+// sample-interleaved (il images)
+template <int V, int LPR, int PPT, bool IL>
 __global__ void __launch_bounds__(BQ_THREADS, 2)
 bp_tile_kernel(const BqParams P)
 {
@@ -245,6 +246,24 @@ bp_tile_kernel(const BqParams P)
     // (when they fit in a few registers; taller tiles load them in the epilogue).
     constexpr bool PREF = PPT * V <= 8;
     float pa1[PREF ? PPT : 1][V], pa2[PREF ? PPT : 1][V];
+    if (IL) {
+        if (PREF && warp < BQ_NW) {
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) {
+                const int k0 = k0b + m;
+                const bool live = k0 < P.n0 && k1 < P.n1 && wy * PPT + m < P.th_eff;
+                const size_t o = live ? (((size_t)grp * P.n0 + k0) * P.n1 + k1) * SB + lq * V : 0;
+                VT v1, v2;
+                float *f1 = reinterpret_cast<float *>(&v1), *f2 = reinterpret_cast<float *>(&v2);
+#pragma unroll
+                for (int v = 0; v < V; ++v) f1[v] = f2[v] = 0.f;
+                if (live && P.ep.add1) v1 = *reinterpret_cast<const VT *>(P.ep.add1 + o);
+                if (live && P.ep.add2) v2 = *reinterpret_cast<const VT *>(P.ep.add2 + o);
+#pragma unroll
+                for (int v = 0; v < V; ++v) { pa1[PREF ? m : 0][v] = f1[v]; pa2[PREF ? m : 0][v] = f2[v]; }
+            }
+        }
+    } else
     if (PREF && warp < BQ_NW) {
 #pragma unroll
         for (int m = 0; m < PPT; ++m)
@@ -387,6 +406,57 @@ bp_tile_kernel(const BqParams P)
     float dsum[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) dsum[v] = 0.f;
+    if (IL) {
+        if (warp < BQ_NW && k1 < P.n1) {
+            float bet[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const int b = b0 + lq * V + v;
+                bet[v] = (E.mode == 1 && E.beta && b < P.batch) ? E.beta[b] : 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < PPT; ++m) {
+                const int k0 = k0b + m;
+                if (k0 < P.n0 && wy * PPT + m < P.th_eff) {
+                    const size_t o = (((size_t)grp * P.n0 + k0) * P.n1 + k1) * SB + lq * V;
+                    VT v1, v2, vo, vp;
+                    float *f1 = reinterpret_cast<float *>(&v1), *f2 = reinterpret_cast<float *>(&v2);
+                    float *fo = reinterpret_cast<float *>(&vo), *fp = reinterpret_cast<float *>(&vp);
+                    if (PREF) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) { f1[v] = pa1[PREF ? m : 0][v]; f2[v] = pa2[PREF ? m : 0][v]; }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) f1[v] = f2[v] = 0.f;
+                        if (E.add1) v1 = *reinterpret_cast<const VT *>(E.add1 + o);
+                        if (E.add2) v2 = *reinterpret_cast<const VT *>(E.add2 + o);
+                    }
+                    if (E.mode == 1) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            const float pn = E.beta ? fmaf(bet[v], f2[v], f1[v]) : f1[v];     // p = r + beta p
+                            const float dv = fmaf(E.c_acc, acc[m][v], pn);                    // d = p + gamma A*(q)
+                            fp[v] = pn; fo[v] = dv;
+                            dsum[v] = fmaf(pn, dv, dsum[v]);
+                        }
+                        *reinterpret_cast<VT *>(E.out2 + o) = vp;
+                        *reinterpret_cast<VT *>(P.out + o) = vo;
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) {
+                            float val = E.c_acc * acc[m][v];
+                            if (E.add1) val = fmaf(E.c1, f1[v], val);
+                            if (E.add2) val = fmaf(E.c2, f2[v], val);
+                            fo[v] = val;
+                            dsum[v] += val * (E.dot_with_add1 ? f1[v] : val);
+                        }
+                        *reinterpret_cast<VT *>(P.out + o) = vo;
+                        if (E.out2) *reinterpret_cast<VT *>(E.out2 + o) = vo;
+                    }
+                }
+            }
+        }
+    } else
     if (warp < BQ_NW && k1 < P.n1) {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -503,12 +573,12 @@ size_t scd_sino_il_bytes(const scd_geom *g, int batch)
     return need + 256;
 }
 
-template <int V, int LPR, int PPT>
+template <int V, int LPR, int PPT, bool IL>
 static int bq_launch_t(const BqParams &P, const BqConfig &c, cudaStream_t st, int device)
 {
     static ScdSmemAttr attr = {};        // per instantiation
-    SCD_CUDA(scd_ensure_smem(bp_tile_kernel<V, LPR, PPT>, attr, device, c.smem));
-    SCD_CUDA(scd_launch_kernel(bp_tile_kernel<V, LPR, PPT>, c.grid, dim3(BQ_THREADS), c.smem, st, 0, P));
+    SCD_CUDA(scd_ensure_smem(bp_tile_kernel<V, LPR, PPT, IL>, attr, device, c.smem));
+    SCD_CUDA(scd_launch_kernel(bp_tile_kernel<V, LPR, PPT, IL>, c.grid, dim3(BQ_THREADS), c.smem, st, 0, P));
     SCD_LAUNCH_CHECK("bp_tile_kernel");
     return 0;
 }
@@ -547,7 +617,14 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     if (ep.n_bands) c.smem = std::max(c.smem, (size_t)c.SB * c.TH * 33 * 4);     // staging tile of the banded epilogue
     const int WY = BQ_NW / c.LPR;
     (void)WY;
-#define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP>(P, c, st, g->device);
+    if (ep.il) {
+        if (c.V != 4 || ep.n_bands) { scd_set_error("scd_bp: interleaved images need groups of >= 4 samples and no bands"); return SCD_E_INVALID; }
+        if (ep.mode == 1 && (!ep.add1 || !ep.out2 || (ep.beta && !ep.add2))) { scd_set_error("scd_bp: direction step needs r, p"); return SCD_E_INVALID; }
+#define BQ_CASE_IL(LL, PP) if (c.LPR == LL && c.PPT == PP) return bq_launch_t<4, LL, PP, true>(P, c, st, g->device);
+        BQ_CASE_IL(1, 1) BQ_CASE_IL(1, 2) BQ_CASE_IL(2, 1) BQ_CASE_IL(2, 2) BQ_CASE_IL(2, 4) BQ_CASE_IL(4, 2) BQ_CASE_IL(4, 4)
+#undef BQ_CASE_IL
+    }
+#define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP, false>(P, c, st, g->device);
     BQ_CASE(1, 1, 1) BQ_CASE(1, 1, 2) BQ_CASE(2, 1, 1) BQ_CASE(2, 1, 2) BQ_CASE(4, 1, 1) BQ_CASE(4, 1, 2)
     BQ_CASE(4, 2, 1) BQ_CASE(4, 2, 2) BQ_CASE(4, 2, 4) BQ_CASE(4, 4, 2) BQ_CASE(4, 4, 4)
 #undef BQ_CASE

@@ -7,8 +7,14 @@
 //   repeat n_iter: d = op(p); alpha = rr/<p,d>; x += alpha p; r -= alpha d;
 //                  rr' = ||r||^2; beta = rr'/rr; p = r + beta p
 // with op(v) = v + gamma*A*(A v) (src/samplers/utils.py:188-189).
-// Launches per iteration: fp_packq (p-update fused), fp_march, bp_tile(+axpy,+<p,d>), cg_update_xr
-// (the last p-update is skipped: its result is never read).
+// Groups of >= 4 samples (batch >= 3): the vectors x, r, p, d, b are sample-interleaved images for the whole
+// solve (il_ops.cu) and an iteration is THREE launches with no packed copy of anything:
+//   fp_march   q = A r + beta q          (q_k = A p_k with p_k = r_k + beta p_{k-1}: the projector reads r through
+//                                         tensor copies, its output phase carries the recurrence and forms beta)
+//   bp_tile    p = r + beta p;  d = p + gamma A*(q);  partial <p,d>      (all in the backprojector's epilogue)
+//   cg_update_xr_il   alpha = rr/<p,d>;  x += alpha p;  r -= alpha d;  partial ||r||^2
+// Batches of 1 or 2 samples (pixels below the 16-byte granule of a tensor copy) keep the packed-copy sequence:
+// fp_packq (p-update fused), fp_march, bp_tile(+axpy,+<p,d>), cg_update_xr (the last p-update is skipped).
 #include "scd_internal.cuh"
 #include <algorithm>
 #include <cstring>
@@ -16,6 +22,8 @@
 struct CgLayout {
     size_t img, sino, part_stride;
     size_t off_q, off_r, off_p, off_d, off_b, off_xh, off_part, off_pack, pack_bytes, total;
+    // interleaved-state solve (same buffer, other carving): five il images, partial sums, beta
+    size_t il_bytes, il_q, il_x, il_r, il_p, il_d, il_b, il_part, il_beta, il_total;
 };
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -27,7 +35,7 @@ static CgLayout cg_layout(const scd_geom *g, int batch)
     L.sino = (size_t)g->n_angles * g->n_det;
     const int nbp = scd_bp_ctas_per_sample_max(g, batch);
     const int nvec = scd_vec_blocks_per_sample((int64_t)L.img, batch);
-    L.part_stride = (size_t)std::max(nbp, nvec);
+    L.part_stride = (size_t)std::max(std::max(nbp, nvec), scd_il_vec_blocks(g, batch));
     size_t o = 0;
     // q = A p lives in the sample-interleaved layout the backprojector stages from
     L.off_q = o;  o += align256(scd_sino_il_bytes(g, batch));
@@ -40,6 +48,19 @@ static CgLayout cg_layout(const scd_geom *g, int batch)
     L.pack_bytes = scd_fp_scratch_need(g, batch);
     L.off_pack = o; o += align256(L.pack_bytes);
     L.total = o;
+    // il carving
+    L.il_bytes = align256(scd_il_image_bytes(g, batch));
+    o = 0;
+    L.il_q = o; o += align256(scd_sino_il_bytes(g, batch));
+    L.il_x = o; o += L.il_bytes;
+    L.il_r = o; o += L.il_bytes;
+    L.il_p = o; o += L.il_bytes;
+    L.il_d = o; o += L.il_bytes;
+    L.il_b = o; o += L.il_bytes;
+    L.il_part = o; o += align256(3 * L.part_stride * batch * 4);
+    L.il_beta = o; o += align256((size_t)batch * 4);
+    L.il_total = o;
+    L.total = std::max(L.total, L.il_total);
     return L;
 }
 
@@ -119,9 +140,82 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
     return 0;
 }
 
+// ---- interleaved-state solve ---------------------------------------------------------------------
+// On entry the il images at L.il_x (start iterate) and L.il_b (right-hand side) are filled; on exit L.il_x holds
+// the result.
+static int cg_run_il(const scd_geom *g, const CgLayout &L, float gamma, int n_iter, int batch, char *w, cudaStream_t st)
+{
+    float *q = (float *)(w + L.il_q), *x = (float *)(w + L.il_x), *r = (float *)(w + L.il_r);
+    float *p = (float *)(w + L.il_p), *d = (float *)(w + L.il_d), *b = (float *)(w + L.il_b);
+    float *part = (float *)(w + L.il_part), *beta = (float *)(w + L.il_beta);
+    const int ps = (int)L.part_stride;
+    float *rr_a = part, *rr_b = part + (size_t)ps * batch, *pd = part + 2 * (size_t)ps * batch;
+    const int nbp = scd_bp_ctas_per_sample(g, batch);
+    const int nvec = scd_il_vec_blocks(g, batch);
+    if (nbp > ps || nvec > ps) {
+        scd_set_error("scd_cg: %d partial sums per sample exceed the workspace stride %d", std::max(nbp, nvec), ps);
+        return SCD_E_INVALID;
+    }
+    const float gs = gamma * (float)g->adj_scale;
+    const int na = g->n_angles;
+    int rc;
+    // r = b - x - gamma A*(A x);  rr = ||r||^2
+    if ((rc = scd_launch_fp_ilimg(g, x, nullptr, q, batch, 0, na, st, nullptr))) return rc;
+    BpEpilogue e0;
+    e0.il = 1; e0.mode = 0;
+    e0.c_acc = -gs; e0.add1 = x; e0.c1 = -1.f; e0.add2 = b; e0.c2 = 1.f;
+    e0.out2 = nullptr; e0.dot_part = rr_a; e0.dot_stride = ps; e0.dot_with_add1 = 0;
+    if ((rc = scd_launch_bp_il(g, q, r, batch, 0, na, e0, st))) return rc;
+    float *rr_new = rr_a, *rr_old = rr_b;          // newest ||r||^2 partials / the ones before
+    int rr_new_n = nbp, rr_old_n = 0;
+    for (int it = 0; it < n_iter; ++it) {
+        // q = A r + beta q   (= A p with p = r + beta p; first iteration: p = r)
+        FpAccumulate acc;
+        acc.rr_new_part = rr_new; acc.rr_new_n = rr_new_n; acc.rr_old_part = rr_old; acc.rr_old_n = rr_old_n;
+        acc.part_stride = ps; acc.beta_out = beta;
+        if ((rc = scd_launch_fp_ilimg(g, r, nullptr, q, batch, 0, na, st, it > 0 ? &acc : nullptr))) return rc;
+        // p = r + beta p;  d = p + gamma A*(q);  pd = <p,d>
+        BpEpilogue e1;
+        e1.il = 1; e1.mode = 1;
+        e1.c_acc = gs; e1.add1 = r; e1.c1 = 1.f; e1.add2 = it > 0 ? p : nullptr; e1.c2 = 0.f;
+        e1.beta = it > 0 ? beta : nullptr;
+        e1.out2 = p; e1.dot_part = pd; e1.dot_stride = ps; e1.dot_with_add1 = 0;
+        if ((rc = scd_launch_bp_il(g, q, d, batch, 0, na, e1, st))) return rc;
+        // alpha = rr/pd;  x += alpha p;  r -= alpha d;  rr' = ||r||^2
+        if ((rc = scd_launch_cg_update_xr_il(g, x, r, p, d, rr_new, rr_new_n, pd, nbp, ps, rr_old, batch, st))) return rc;
+        std::swap(rr_new, rr_old);                 // the kernel wrote the newest partials into the older array
+        rr_old_n = rr_new_n;
+        rr_new_n = nvec;
+    }
+    return 0;
+}
+
+static int cg_check(const scd_geom *g, const void *work, size_t work_bytes, int n_iter, const CgLayout &L, const char *who)
+{
+    if (n_iter < 0) { scd_set_error("%s: n_iter < 0", who); return SCD_E_INVALID; }
+    if (((uintptr_t)work & 255) != 0) { scd_set_error("%s: workspace must be 256-byte aligned", who); return SCD_E_INVALID; }
+    if (work_bytes < L.total) {
+        scd_set_error("%s: workspace too small (%zu < %zu bytes)", who, work_bytes, L.total);
+        return SCD_E_WORKSPACE;
+    }
+    (void)g;
+    return 0;
+}
+
 extern "C" int scd_cg(const scd_geom_t *g, float *x, const float *rhs, double gamma, int n_iter,
                       int batch, void *work, size_t work_bytes, void *stream)
 {
+    if (g && x && rhs && work && batch > 0 && scd_il_image_ok(g, batch)) {
+        const CgLayout L = cg_layout(g, batch);
+        int rc = cg_check(g, work, work_bytes, n_iter, L, "scd_cg");
+        if (rc) return rc;
+        if (n_iter == 0) return 0;                // the result is the start iterate (x is updated in place)
+        char *w = (char *)work;
+        cudaStream_t st = (cudaStream_t)stream;
+        if ((rc = scd_launch_il_pack(g, x, (float *)(w + L.il_x), rhs, (float *)(w + L.il_b), batch, st))) return rc;
+        if ((rc = cg_run_il(g, L, (float)gamma, n_iter, batch, w, st))) return rc;
+        return scd_launch_il_unpack(g, (const float *)(w + L.il_x), x, batch, st);
+    }
     return scd_cg_run(g, x, x, rhs, (float)gamma, n_iter, batch, work, work_bytes, (cudaStream_t)stream, nullptr);
 }
 
@@ -163,6 +257,64 @@ extern "C" int scd_bp_il(const scd_geom_t *g, const float *sino_il, float *out, 
     e.c_acc = c_acc; e.add1 = addend; e.c1 = c_add; e.add2 = nullptr; e.c2 = 0.f;
     e.out2 = nullptr; e.dot_part = nullptr; e.dot_stride = 0; e.dot_with_add1 = 0;
     return scd_launch_bp_il(g, sino_il, out, batch, angle_lo, angle_hi, e, (cudaStream_t)stream);
+}
+
+// ---- sample-interleaved images at the ABI (callers that keep their vectors in the library's layout) ----
+extern "C" size_t scd_img_il_bytes(const scd_geom_t *g, int batch)
+{
+    if (!g || batch <= 0 || !scd_il_image_ok(g, batch)) return 0;
+    return scd_il_image_bytes(g, batch);
+}
+
+static int il_args_ok(const scd_geom_t *g, const void *a, const void *b, int batch, const char *who)
+{
+    if (!g || !a || !b) { scd_set_error("%s: null argument", who); return SCD_E_INVALID; }
+    if (batch < 0) { scd_set_error("%s: negative batch", who); return SCD_E_INVALID; }
+    if (batch > 0 && !scd_il_image_ok(g, batch)) {
+        scd_set_error("%s: batches of %d sample(s) have no interleaved-image form (scd_img_il_bytes returns 0)", who, batch);
+        return SCD_E_INVALID;
+    }
+    return 0;
+}
+
+extern "C" int scd_img_il_pack(const scd_geom_t *g, const float *img, float *img_il, int batch, void *stream)
+{
+    int rc = il_args_ok(g, img, img_il, batch, "scd_img_il_pack");
+    if (rc || batch == 0) return rc;
+    if (((uintptr_t)img_il & 127) != 0) { scd_set_error("scd_img_il_pack: img_il must be 128-byte aligned"); return SCD_E_INVALID; }
+    return scd_launch_il_pack(g, img, img_il, nullptr, nullptr, batch, (cudaStream_t)stream);
+}
+
+extern "C" int scd_img_il_unpack(const scd_geom_t *g, const float *img_il, float *img, int batch, void *stream)
+{
+    int rc = il_args_ok(g, img_il, img, batch, "scd_img_il_unpack");
+    if (rc || batch == 0) return rc;
+    return scd_launch_il_unpack(g, img_il, img, batch, (cudaStream_t)stream);
+}
+
+extern "C" int scd_fp_ilimg(const scd_geom_t *g, const float *img_il, float *sino_il, int batch,
+                            int angle_lo, int angle_hi, void *stream)
+{
+    int rc = il_args_ok(g, img_il, sino_il, batch, "scd_fp_ilimg");
+    if (rc || batch == 0) return rc;
+    if (((uintptr_t)sino_il & 127) != 0) { scd_set_error("scd_fp_ilimg: sino_il must be 128-byte aligned"); return SCD_E_INVALID; }
+    return scd_launch_fp_ilimg(g, img_il, nullptr, sino_il, batch, angle_lo, angle_hi, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int scd_bp_ilimg(const scd_geom_t *g, const float *sino_il, float *out_il, int batch,
+                            int angle_lo, int angle_hi, float c_acc, const float *addend_il, float c_add, void *stream)
+{
+    int rc = il_args_ok(g, sino_il, out_il, batch, "scd_bp_ilimg");
+    if (rc || batch == 0) return rc;
+    if (((uintptr_t)sino_il & 127) != 0 || ((uintptr_t)out_il & 15) != 0 || ((uintptr_t)addend_il & 15) != 0) {
+        scd_set_error("scd_bp_ilimg: misaligned buffer"); return SCD_E_INVALID;
+    }
+    if (angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) { scd_set_error("scd_bp_ilimg: bad angle range"); return SCD_E_INVALID; }
+    BpEpilogue e;
+    e.il = 1; e.mode = 0;
+    e.c_acc = c_acc; e.add1 = addend_il; e.c1 = c_add; e.add2 = nullptr; e.c2 = 0.f;
+    e.out2 = nullptr; e.dot_part = nullptr; e.dot_stride = 0; e.dot_with_add1 = 0;
+    return scd_launch_bp_il(g, sino_il, out_il, batch, angle_lo, angle_hi, e, (cudaStream_t)stream);
 }
 
 extern "C" size_t scd_bp_scratch_bytes(const scd_geom_t *g, int batch)
@@ -222,9 +374,19 @@ extern "C" int scd_dds_step(const scd_geom_t *g, const float *x, const float *s,
         return SCD_E_WORKSPACE;
     }
     char *w = (char *)work;
+    int rc;
+    if (scd_il_image_ok(g, batch)) {
+        // Tweedie writes xhat0 for the caller and the CG start iterate / right-hand side as il images; DDIM reads
+        // the CG result in that layout: 1 + 2 + 3*n_iter + 1 launches
+        if ((rc = cg_check(g, work, work_bytes, n_iter, L, "scd_dds_step"))) return rc;
+        if ((rc = scd_launch_tweedie_il(g, x, s, atb, t, abar, n_table, (float)gamma, xhat0, (float *)(w + L.il_x),
+                                        (float *)(w + L.il_b), batch, st))) return rc;
+        if (n_iter > 0 && (rc = cg_run_il(g, L, (float)gamma, n_iter, batch, w, st))) return rc;
+        return scd_launch_ddim_il(g, (const float *)(w + L.il_x), s, eps, t, t_prev, abar, n_table, (float)eta,
+                                  (float)(eta * eta), x_next, batch, st);
+    }
     float *b = (float *)(w + L.off_b), *xh = (float *)(w + L.off_xh);
     const int64_t numel = (int64_t)L.img;
-    int rc;
     // xhat0 = Tweedie(x, s) and b = xhat0 + gamma*A*y are produced inside the pack pass of the
     // first projection; CG starts from xhat0 but must not overwrite it (the predictor returns it)
     FpPrologue tw;

@@ -21,10 +21,24 @@
 //   strips        TR rows of the packed image = one contiguous byte range, fetched by a
 //                 producer warp with cp.async.bulk (TMA unit) into an mbarrier ring
 //                 (full/empty barriers; no CTA-wide barrier inside the march).
+//   il image      groups of >= 4 samples need no packed copy at all: the image is kept
+//                 sample-interleaved, img_il[group][k0][k1][SB] (no pads), and every strip row is
+//                 fetched by a 4-D TENSOR copy (cp.async.bulk.tensor.4d, SASS UTMALDG): class 0 (rows =
+//                 image rows) takes boxes {SB, pixels, 1, 1} into the strip layout [row][pixel][SB]
+//                 of the packed path; class 1 (rows = image columns) takes boxes {SB, TR, pixels, 1}
+//                 -- TR*SB*4-byte pieces gathered with the image's row stride -- which land
+//                 PIXEL-MAJOR, [pixel][row][SB]: the transposed orientation is never materialised in
+//                 HBM.  Zero pad pixels / pad rows come from the unit's out-of-bounds fill.  In the
+//                 pixel-major layout the rays of a quarter-warp visit the rows of a strip in
+//                 different (XOR-rotated) orders, so their 128-byte wavefront never collides
+//                 whatever the ray spacing (the row-major layout conflicts when two rays are two
+//                 pixels apart).  Inside CG the vectors live in this layout for the whole solve
+//                 (cg_solver.cu).
 //   cluster       for small batches the rows are split over a cluster of CS CTAs; partial line
 //                 integrals are exchanged through distributed shared memory and added in rank
 //                 order (deterministic, no atomics).
 #include "scd_internal.cuh"
+#include <cuda.h>                 // CUtensorMap (the encoder is fetched through the runtime: no libcuda link)
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
@@ -71,6 +85,16 @@ struct MqParams {
     MqLayout L;
     int n_runs;
     MqRun runs[MQ_MAX_RUNS];
+    // tensor-copy source (tma != 0): strip rows come from the sample-interleaved image through the two tensor
+    // maps passed next to this struct; spitch = pixels per shared-memory strip row (nbox boxes of bw pixels)
+    int tma;
+    int spitch[2], nbox[2], bw[2];
+    // output recurrence of the CG solve (acc_mode != 0): q = A r + beta q_old with
+    // beta = sum(rr_new_part) / sum(rr_old_part) per sample (q_{k} = A p_k, p_k = r_k + beta p_{k-1});
+    // the per-sample beta is also stored to beta_out for the backprojector's direction update
+    int acc_mode;
+    const float *rr_new_part; int rr_new_n; const float *rr_old_part; int rr_old_n; int part_stride;
+    float *beta_out;
 };
 
 // ------------------------------------------------------------------ pack ---
@@ -244,6 +268,15 @@ __device__ __forceinline__ void mq_bulk_g2s(void *dst, const void *src, unsigned
                  :: "r"(mq_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mq_smem_u32(bar)) : "memory");
 }
 
+// 4-D tiled tensor copy global -> shared through the TMA unit (SASS UTMALDG), completion on an mbarrier;
+// elements outside the tensor are filled with zeros
+__device__ __forceinline__ void mq_tensor_g2s(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
+                                              unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+                 :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mq_smem_u32(bar)) : "memory");
+}
+
 // Tap loads with explicit 32-bit shared-window addresses (a generic pointer would be re-mapped
 // through the cluster window on every access).  volatile: they stay behind the mbarrier wait.
 template <int V> struct MqVec;
@@ -289,6 +322,79 @@ __device__ __forceinline__ void mq_tap(float (&p)[4], float4 l, float4 r, float 
     p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
 }
 
+// The march of one warp over the strips of its CTA.  PM = pixel-major strips [pixel][row][SB] (tensor copies of
+// class 1): the pixel stride is the compile-time TR*SB*4 and every ray visits the rows of a strip in the order
+// rr ^ rot, rot = (ray index) mod (rays per quarter-warp) -- the rays that share a 128-byte wavefront then read
+// different rows, i.e. different bank groups, wherever their pixels are.  Row-major strips: rot = 0.
+template <int V, int LPR, int NSLOT, int TR, int NW, bool PM>
+__device__ __forceinline__ void mq_march_rows(float (&acc)[NSLOT][V], const int (&eidx)[NSLOT], unsigned livemask, int NCH,
+                                              int warp, int lane, int nst, int NBUF, int r_begin, int ncols,
+                                              unsigned row_bytes, unsigned strip_bytes, unsigned char *tile0,
+                                              const float2 *rays, unsigned long long *full, unsigned long long *empty,
+                                              unsigned long long *dbg)
+{
+    typedef MqVec<V> LD;
+    typedef typename LD::T VT;
+    constexpr int SB = V * LPR;
+    constexpr unsigned PS = PM ? TR * SB * 4 : SB * 4;           // bytes between neighbouring pixels of a row
+    constexpr int QR = 8 / LPR < TR ? 8 / LPR : TR;              // rows the rotation spreads a quarter-warp over
+    const int lr = lane / LPR, lq = lane - lr * LPR;
+    const int rot = PM ? (lr & (QR - 1)) : 0;
+    float cf[TR];                                                // row visited at unrolled step rr, as a float ...
+    unsigned ro[TR];                                             // ... and its byte offset inside the strip
+#pragma unroll
+    for (int rr = 0; rr < TR; ++rr) {
+        cf[rr] = (float)(rr ^ rot);
+        ro[rr] = PM ? (unsigned)((rr ^ rot) * SB * 4) : (unsigned)rr * row_bytes;
+    }
+    const float zmax = (float)(ncols + 1);    // u = ncols: both taps on the right pads
+    // shared-window address of this lane's samples in pixel 0 of row 0 of buffer 0, with the
+    // mantissa offset of the floor trick folded in
+    const unsigned lane_base = mq_smem_u32(tile0) + (unsigned)(lq * V * 4) - (unsigned)MQ_MAGIC_BITS * PS;
+    const unsigned rays_base = mq_smem_u32(rays);
+    int bi = 0; unsigned ph = 0;
+    for (int st = 0; st < nst; ++st) {
+        mq_mbar_wait(&full[bi], ph);
+        if (st == 0) scd_stamp(dbg, 3);       // first strip landed (warp 0)
+        const unsigned sbuf = lane_base + (unsigned)bi * strip_bytes;
+        const float r0f = (float)(r_begin + st * TR);
+#pragma unroll
+        for (int k = 0; k < NSLOT; ++k) {
+            if (warp + k * NW < NCH) {                              // warp-uniform
+                const float2 ub = MqVec<2>::ld<0>(rays_base + (unsigned)eidx[k] * 8u);
+                const float bf = ub.y;
+                const float z0 = fmaf(r0f, bf, ub.x);
+                const float z1 = fmaf((float)(TR - 1), bf, z0);
+                // every ray of this chunk outside the image on every row of the strip
+                const bool outside = !((livemask >> k) & 1u) || fmaxf(z0, z1) <= 0.0f || fminf(z0, z1) >= zmax;
+                if (!__all_sync(0xffffffffu, outside)) {
+                    float w[TR];
+                    unsigned ad[TR];
+#pragma unroll
+                    for (int rr = 0; rr < TR; ++rr) {
+                        // clamped position: outside the image both taps land on zero pad pixels
+                        const float z = fminf(fmaxf(fmaf(cf[rr], bf, z0), 0.0f), zmax);
+                        const float t = __fadd_rd(z, MQ_MAGIC);       // floor(z) in the mantissa
+                        w[rr] = z - (t - MQ_MAGIC);
+                        ad[rr] = sbuf + ro[rr] + (unsigned)__float_as_int(t) * PS;
+                    }
+                    VT tl[TR], tr[TR];
+#pragma unroll
+                    for (int rr = 0; rr < TR; ++rr) {
+                        tl[rr] = LD::template ld<0>(ad[rr]);
+                        tr[rr] = LD::template ld<PS>(ad[rr]);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < TR; ++rr) mq_tap(acc[k], tl[rr], tr[rr], 1.0f - w[rr], w[rr]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mq_mbar_arrive(&empty[bi]);                   // this warp is done with buffer bi
+        if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+    }
+}
+
 struct __align__(8) MqAng { float scale; int id; };
 
 // V     samples per lane (vector width of a tap)
@@ -298,7 +404,7 @@ struct __align__(8) MqAng { float scale; int id; };
 // NWT   warps per CTA: NWT-1 marching warps + one producer warp
 template <int V, int LPR, int NSLOT, int TR, int NWT>
 __global__ void __launch_bounds__(32 * NWT, 1)
-fp_march_kernel(const MqParams P)
+fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1)
 {
     typedef MqVec<V> LD;
     typedef typename LD::T VT;
@@ -333,7 +439,7 @@ fp_march_kernel(const MqParams P)
     const int cls = R.cls;
     const int nrows = cls == 0 ? P.n0 : P.n1;   // marching axis
     const int ncols = cls == 0 ? P.n1 : P.n0;   // interpolation axis
-    const int pitch = P.L.pitch[cls];
+    const int pitch = P.tma ? P.spitch[cls] : P.L.pitch[cls];   // pixels per strip row in shared memory
     const int n_det = P.n_det;
     const int b0 = grp * SB;
     const unsigned row_bytes = (unsigned)(pitch * SB * 4);
@@ -353,10 +459,11 @@ fp_march_kernel(const MqParams P)
     MqAng *ang = reinterpret_cast<MqAng *>(empty + MQ_MAX_NBUF);
     float2 *rays = reinterpret_cast<float2 *>(ang + P.NA);
     float *red = reinterpret_cast<float *>(smem_raw);
+    __shared__ float betas[16];
 
     const int E = na * n_det;
-    const float *src = P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[cls] +
-                       (size_t)r_begin * pitch * SB;
+    const float *src = P.tma ? nullptr : P.packed + (size_t)grp * P.L.group_floats + P.L.cls_off[cls] +
+                                         (size_t)r_begin * pitch * SB;
 
     scd_stamp(P.dbg, 0);                          // CTA start
     if (tid == 0) {
@@ -398,7 +505,32 @@ fp_march_kernel(const MqParams P)
 
     if (warp == NW) {
         // ------------------------------ producer warp ------------------------------
-        if (lane == 0) {
+        if (P.tma) {
+            // Class 0 (rows = image rows): one tensor copy per (strip row, box of bw pixels), lane = rr * nbox + box,
+            // landing row-major [row][pixel][SB].  Class 1 (rows = image columns): one copy per box covering all TR
+            // rows, box {SB, TR, bw}: the unit gathers TR*SB*4-byte pieces with the image's row stride and lands
+            // them pixel-major [pixel][row][SB].  Pixel -1, pixels >= ncols and rows >= nrows are out of bounds:
+            // zero fill.
+            const CUtensorMap *tm = cls == 0 ? &tm0 : &tm1;
+            const int nbox = P.nbox[cls], bw = P.bw[cls];
+            const int rr = cls == 0 ? lane / nbox : 0, bx = cls == 0 ? lane - rr * nbox : lane;
+            const bool mine = cls == 0 ? lane < TR * nbox : lane < nbox;
+            const unsigned dst0 = mq_smem_u32(tile0) +
+                (cls == 0 ? (unsigned)rr * row_bytes + (unsigned)(bx * bw * SB * 4) : (unsigned)(bx * bw) * (unsigned)(TR * SB * 4));
+            const int cpix = bx * bw - 1;
+            int bi = 0; unsigned ph = 0;
+            for (int st = 0; st < nst; ++st) {
+                if (st >= NBUF) mq_mbar_wait(&empty[bi], ph ^ 1u);      // previous use of this buffer released
+                if (lane == 0) mq_mbar_expect_tx(&full[bi], strip_bytes);
+                __syncwarp();
+                if (mine) {
+                    const int row = r_begin + st * TR + rr;
+                    if (cls == 0) mq_tensor_g2s(dst0 + (unsigned)bi * strip_bytes, tm, 0, cpix, row, grp, &full[bi]);
+                    else          mq_tensor_g2s(dst0 + (unsigned)bi * strip_bytes, tm, 0, row, cpix, grp, &full[bi]);
+                }
+                if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+            }
+        } else if (lane == 0) {
             int bi = 0; unsigned ph = 0;
             for (int st = 0; st < nst; ++st) {
                 if (st >= NBUF) mq_mbar_wait(&empty[bi], ph ^ 1u);      // previous use of this buffer released
@@ -409,52 +541,34 @@ fp_march_kernel(const MqParams P)
         }
     } else {
         // ------------------------------ marching warps -----------------------------
-        const float zmax = (float)(ncols + 1);    // u = ncols: both taps on the right pads
-        // shared-window address of this lane's samples in pixel 0 of row 0 of buffer 0, with the
-        // mantissa offset of the floor trick folded in
-        const unsigned lane_base = mq_smem_u32(tile0) + (unsigned)(lq * V * 4) - (unsigned)MQ_MAGIC_BITS * (unsigned)(SB * 4);
-        const unsigned rays_base = mq_smem_u32(rays);
-        int bi = 0; unsigned ph = 0;
-        for (int st = 0; st < nst; ++st) {
-            mq_mbar_wait(&full[bi], ph);
-            if (st == 0) scd_stamp(P.dbg, 3);     // first strip landed (warp 0)
-            const unsigned sbuf = lane_base + (unsigned)bi * strip_bytes;
-            const float r0f = (float)(r_begin + st * TR);
+        if (P.acc_mode) {
+            // beta of this group's samples from the per-block partial sums (fixed order: deterministic); the
+            // loads overlap the flight of the first strip
+            for (int s = warp; s < SB; s += NW) {
+                const int b = b0 + s;
+                float rn = 0.f, ro = 0.f;
+                if (b < P.batch) {
+                    for (int i = lane; i < P.rr_new_n; i += 32) rn += P.rr_new_part[(size_t)b * P.part_stride + i];
+                    for (int i = lane; i < P.rr_old_n; i += 32) ro += P.rr_old_part[(size_t)b * P.part_stride + i];
+                }
 #pragma unroll
-            for (int k = 0; k < NSLOT; ++k) {
-                if (warp + k * NW < NCH) {                              // warp-uniform
-                    const float2 ub = MqVec<2>::ld<0>(rays_base + (unsigned)eidx[k] * 8u);
-                    const float bf = ub.y;
-                    const float z0 = fmaf(r0f, bf, ub.x);
-                    const float z1 = fmaf((float)(TR - 1), bf, z0);
-                    // every ray of this chunk outside the image on every row of the strip
-                    const bool outside = !((livemask >> k) & 1u) || fmaxf(z0, z1) <= 0.0f || fminf(z0, z1) >= zmax;
-                    if (!__all_sync(0xffffffffu, outside)) {
-                        float w[TR];
-                        unsigned ad[TR];
-#pragma unroll
-                        for (int rr = 0; rr < TR; ++rr) {
-                            // clamped position: outside the image both taps land on zero pad pixels
-                            const float z = fminf(fmaxf(fmaf((float)rr, bf, z0), 0.0f), zmax);
-                            const float t = __fadd_rd(z, MQ_MAGIC);       // floor(z) in the mantissa
-                            w[rr] = z - (t - MQ_MAGIC);
-                            ad[rr] = sbuf + rr * row_bytes + (unsigned)__float_as_int(t) * (unsigned)(SB * 4);
-                        }
-                        VT tl[TR], tr[TR];
-#pragma unroll
-                        for (int rr = 0; rr < TR; ++rr) {
-                            tl[rr] = LD::template ld<0>(ad[rr]);
-                            tr[rr] = LD::template ld<SB * 4>(ad[rr]);
-                        }
-#pragma unroll
-                        for (int rr = 0; rr < TR; ++rr) mq_tap(acc[k], tl[rr], tr[rr], 1.0f - w[rr], w[rr]);
-                    }
+                for (int off = 16; off > 0; off >>= 1) {
+                    rn += __shfl_xor_sync(0xffffffffu, rn, off);
+                    ro += __shfl_xor_sync(0xffffffffu, ro, off);
+                }
+                if (lane == 0) {
+                    const float be = b < P.batch ? __fdiv_rn(rn, ro) : 0.f;
+                    betas[s] = be;
+                    if (unit == 0 && rank == 0 && b < P.batch && P.beta_out) P.beta_out[b] = be;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mq_mbar_arrive(&empty[bi]);                   // this warp is done with buffer bi
-            if (++bi == NBUF) { bi = 0; ph ^= 1u; }
         }
+        if (P.tma && cls == 1)
+            mq_march_rows<V, LPR, NSLOT, TR, NW, true>(acc, eidx, livemask, NCH, warp, lane, nst, NBUF, r_begin, ncols,
+                                                       row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg);
+        else
+            mq_march_rows<V, LPR, NSLOT, TR, NW, false>(acc, eidx, livemask, NCH, warp, lane, nst, NBUF, r_begin, ncols,
+                                                        row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg);
     }
     __syncthreads();                              // all strips consumed: the ring can be reused
     scd_stamp(P.dbg, 4);                          // march done
@@ -502,7 +616,14 @@ fp_march_kernel(const MqParams P)
             float *of = reinterpret_cast<float *>(&ov);
 #pragma unroll
             for (int v = 0; v < V; ++v) of[v] = sum[v] * sc;
-            *reinterpret_cast<VT *>(dst + ((size_t)ang[ai].id * P.il_nb + P.il_padl + j) * SB + q * V) = ov;
+            VT *qp = reinterpret_cast<VT *>(dst + ((size_t)ang[ai].id * P.il_nb + P.il_padl + j) * SB + q * V);
+            if (P.acc_mode) {                       // q = A r + beta * q_old
+                const VT old = *qp;
+                const float *pf = reinterpret_cast<const float *>(&old);
+#pragma unroll
+                for (int v = 0; v < V; ++v) of[v] = fmaf(betas[q * V + v], pf[v], of[v]);
+            }
+            *qp = ov;
         }
         const int npad = P.il_nb - n_det;
         for (int ai = rank; ai < na; ai += CS) {
@@ -541,7 +662,26 @@ struct MqConfig {
     int V, LPR, SB, NSLOT, TR, NWT, NA, CS, nbuf, rows_per_cta, groups;
     MqLayout L;
     size_t smem, scratch_bytes, ring_bytes;
+    int tma, spitch[2], nbox[2], bw[2];      // tensor-copy source: shared-memory strip rows of nbox boxes x bw pixels
 };
+
+// Strip-row geometry of the tensor-copy path: ncols + 3 pixels (1 zero pixel left, 2 right) split into boxes of at
+// most 256 pixels (the box limit of a tensor map) whose byte size is a multiple of 128 (alignment of the copy's
+// shared-memory destination)
+static void mq_tma_rows(const scd_geom *g, int SB, int spitch[2], int nbox[2], int bw[2])
+{
+    const int nc[2] = {g->n1, g->n0};
+    const int gran = std::max(1, 32 / SB);
+    for (int c = 0; c < 2; ++c) {
+        const int need = nc[c] + 3;
+        nbox[c] = (need + 255) / 256;
+        int w = (need + nbox[c] - 1) / nbox[c];
+        w = ((w + gran - 1) / gran) * gran;
+        if (w > 256) { nbox[c] += 1; w = (need + nbox[c] - 1) / nbox[c]; w = ((w + gran - 1) / gran) * gran; }
+        bw[c] = w;
+        spitch[c] = nbox[c] * w;
+    }
+}
 
 static MqLayout mq_layout(const scd_geom *g, int SB)
 {
@@ -597,13 +737,20 @@ int scd_group_samples(const scd_geom *g, int batch)
     return sb;
 }
 
-static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max)
+static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max, bool tma = false)
 {
     MqConfig c;
     c.SB = scd_group_samples(g, batch);
     c.V = c.SB >= 4 ? 4 : c.SB;
     c.LPR = c.SB / c.V;
-    const int maxpitch = std::max(g->n0, g->n1) + 3;
+    c.tma = tma ? 1 : 0;
+    int maxpitch = std::max(g->n0, g->n1) + 3;
+    if (tma) {
+        mq_tma_rows(g, c.SB, c.spitch, c.nbox, c.bw);
+        maxpitch = std::max(c.spitch[0], c.spitch[1]);
+    } else {
+        for (int k = 0; k < 2; ++k) c.spitch[k] = c.nbox[k] = c.bw[k] = 0;
+    }
     const size_t budget = (size_t)g->smem_optin;
     c.SB = c.V * c.LPR;
     c.groups = (batch + c.SB - 1) / c.SB;
@@ -773,56 +920,57 @@ size_t scd_fp_scratch_need_v4(const scd_geom *g, int batch)
 }
 
 template <int V, int LPR, int NSLOT, int TR, int NWT>
-static int mq_launch_t(const MqParams &P, dim3 grid, size_t smem, cudaStream_t st, int device)
+static int mq_launch_t(const MqParams &P, const CUtensorMap *tms, dim3 grid, size_t smem, cudaStream_t st, int device)
 {
     static ScdSmemAttr attr = {};        // per instantiation
     SCD_CUDA(scd_ensure_smem(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, attr, device, smem));
-    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P));
+    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P, tms[0], tms[1]));
     SCD_LAUNCH_CHECK("fp_march_kernel");
     return 0;
 }
 
-int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
-                     int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
-                     const FpPrologue *prologue)
+// ---- tensor maps of the sample-interleaved image ---------------------------------------------
+typedef CUresult (*MqEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static MqEncodeFn mq_encoder()
 {
-    FpPrologue Q;
-    if (prologue) Q = *prologue; else { memset(&Q, 0, sizeof(Q)); }
-    // angles of each class inside the range
-    int ncls[2] = {0, 0};
-    for (int a = angle_lo; a < angle_hi; ++a) ncls[g->h_fp[a].cls]++;
-    MqConfig c = mq_choose(g, batch, std::max(ncls[0], ncls[1]));
-    if (c.smem > (size_t)g->smem_optin || !c.NSLOT) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
-    const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
-    if (!scratch || sp + c.scratch_bytes > (uintptr_t)scratch + scratch_bytes) {
-        scd_set_error("scd_fp: scratch too small (%zu bytes given, %zu needed; see scd_fp_scratch_bytes)",
-                      scratch_bytes, c.scratch_bytes + 128);
-        return SCD_E_WORKSPACE;
-    }
-    MqParams P;
-    memset(&P, 0, sizeof(P));
-    P.img = img; P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb; P.packed = (float *)sp; P.fp = g->d_fp; P.rayt = g->d_rayt; P.angt = g->d_angt; P.order = g->d_order;
-    P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
-    P.NA = c.NA; P.nbuf = c.nbuf; P.CS = c.CS; P.rows_per_cta = c.rows_per_cta; P.ring_bytes = (int)c.ring_bytes; P.L = c.L;
-    P.need_cls[0] = ncls[0] > 0; P.need_cls[1] = ncls[1] > 0;
-    const unsigned gx = (unsigned)c.groups * c.CS;
+    static MqEncodeFn fn = []() -> MqEncodeFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (MqEncodeFn)p;
+    }();
+    return fn;
+}
 
-    // ---- pack: image -> tile-ready layout (both orientations), producer fused in ----
-    // (fp_skip_pack: benchmarking aid -- march again over the packed copy of the previous call)
-    if (!(g->tune_fp_skip_pack && Q.mode == 0)) {
-        if (c.groups > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
-        dim3 pg((std::max(g->n1, c.L.rows[1]) + PK_T - 1) / PK_T, (std::max(g->n0, c.L.rows[0]) + PK_T - 1) / PK_T, c.groups);
-#define PK_CASE(SS)                                                                                  \
-        if (c.SB == SS) {                                                                               \
-            if (Q.mode == 0) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<0, SS>, pg, dim3(256), 0, st, 0, P, Q));       \
-            else if (Q.mode == 1) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<1, SS>, pg, dim3(256), 0, st, 0, P, Q));  \
-            else SCD_CUDA(scd_launch_kernel(fp_packq_kernel<2, SS>, pg, dim3(256), 0, st, 0, P, Q));                   \
-        }
-        PK_CASE(1) PK_CASE(2) PK_CASE(4) PK_CASE(8) PK_CASE(16)
-#undef PK_CASE
-        SCD_LAUNCH_CHECK("fp_packq_kernel");
+// img_il[group][k0][k1][SB] as a 4-D tensor (SB, n1, n0, groups); class 0 boxes run along k1, class 1 along k0
+static int mq_make_maps(const scd_geom *g, const float *img_il, const MqConfig &c, CUtensorMap tms[2])
+{
+    MqEncodeFn enc = mq_encoder();
+    if (!enc) { scd_set_error("scd_fp: cuTensorMapEncodeTiled is not available in this driver"); return SCD_E_NODEVICE; }
+    const cuuint64_t dims[4] = {(cuuint64_t)c.SB, (cuuint64_t)g->n1, (cuuint64_t)g->n0, (cuuint64_t)c.groups};
+    const cuuint64_t strides[3] = {(cuuint64_t)c.SB * 4, (cuuint64_t)g->n1 * c.SB * 4, (cuuint64_t)g->n0 * g->n1 * c.SB * 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int cls = 0; cls < 2; ++cls) {
+        // class 0: one strip row of bw pixels; class 1: TR image columns x bw pixels (lands pixel-major)
+        const cuuint32_t box[4] = {(cuuint32_t)c.SB, cls == 0 ? (cuuint32_t)c.bw[0] : (cuuint32_t)c.TR,
+                                   cls == 0 ? 1u : (cuuint32_t)c.bw[1], 1u};
+        const CUresult r = enc(&tms[cls], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)img_il, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { scd_set_error("scd_fp: cuTensorMapEncodeTiled failed (%d)", (int)r); return SCD_E_INVALID; }
     }
+    return 0;
+}
 
+// plan (cached) + launch of the march for one configuration; P carries sources / destinations
+static int mq_march(const scd_geom *g, const MqConfig &c, MqParams &P, const CUtensorMap *tms, int angle_lo, int angle_hi,
+                    cudaStream_t st)
+{
     // the plan depends only on the geometry, the configuration and the angle range: keep the last one
     // (the search simulates a few hundred schedules, too slow to repeat at every launch)
     struct PlanKey { unsigned long long g; int lo, hi, groups, NA, CS, plan, sm; };
@@ -841,20 +989,21 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
     P.groups = c.groups; P.n_big = pl.n_big; P.n_units = pl.units; P.dbg = scd_debug_stamps();
     P.n_runs = pl.n_runs;
     for (int i = 0; i < pl.n_runs; ++i) P.runs[i] = pl.runs[i];
+    const unsigned gx = (unsigned)c.groups * c.CS;
     dim3 grid(gx * pl.units);      // linear: see the index decoding at the top of the kernel
     int rc = SCD_E_INVALID;
 #define MQ_CASE(VV, LL, TT)                                                                         \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 16)                                      \
-        rc = c.NSLOT == 6 ? mq_launch_t<VV, LL, 6, TT, 16>(P, grid, c.smem, st, g->device)                     \
-                          : mq_launch_t<VV, LL, 13, TT, 16>(P, grid, c.smem, st, g->device);
+        rc = c.NSLOT == 6 ? mq_launch_t<VV, LL, 6, TT, 16>(P, tms, grid, c.smem, st, g->device)                     \
+                          : mq_launch_t<VV, LL, 13, TT, 16>(P, tms, grid, c.smem, st, g->device);
 #define MQ_CASE24(VV, LL, TT)                                                                       \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 24)                                      \
-        rc = c.NSLOT == 4 ? mq_launch_t<VV, LL, 4, TT, 24>(P, grid, c.smem, st, g->device)                     \
-                          : mq_launch_t<VV, LL, 8, TT, 24>(P, grid, c.smem, st, g->device);
+        rc = c.NSLOT == 4 ? mq_launch_t<VV, LL, 4, TT, 24>(P, tms, grid, c.smem, st, g->device)                     \
+                          : mq_launch_t<VV, LL, 8, TT, 24>(P, tms, grid, c.smem, st, g->device);
 #define MQ_CASE32(VV, LL, TT)                                                                       \
     if (c.V == VV && c.LPR == LL && c.TR == TT && c.NWT == 32)                                      \
-        rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, grid, c.smem, st, g->device)                     \
-                          : mq_launch_t<VV, LL, 6, TT, 32>(P, grid, c.smem, st, g->device);
+        rc = c.NSLOT == 3 ? mq_launch_t<VV, LL, 3, TT, 32>(P, tms, grid, c.smem, st, g->device)                     \
+                          : mq_launch_t<VV, LL, 6, TT, 32>(P, tms, grid, c.smem, st, g->device);
     MQ_CASE(1, 1, 8) MQ_CASE(2, 1, 8) MQ_CASE(4, 1, 8) MQ_CASE(4, 1, 4)
     MQ_CASE(4, 2, 8) MQ_CASE(4, 2, 4) MQ_CASE(4, 4, 4) MQ_CASE(4, 4, 2)
     MQ_CASE24(4, 1, 8) MQ_CASE24(4, 1, 4) MQ_CASE24(4, 2, 8) MQ_CASE24(4, 2, 4) MQ_CASE24(4, 4, 4) MQ_CASE24(4, 4, 2)
@@ -864,6 +1013,115 @@ int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *si
 #undef MQ_CASE32
     if (rc == SCD_E_INVALID) scd_set_error("scd_fp: no kernel for V=%d LPR=%d TR=%d warps=%d", c.V, c.LPR, c.TR, c.NWT);
     return rc;
+}
+
+static void mq_fill_params(const scd_geom *g, const MqConfig &c, MqParams &P, float *sino, float *sino_il, int batch,
+                           const int ncls[2])
+{
+    memset(&P, 0, sizeof(P));
+    P.sino = sino; P.sino_il = sino_il; P.il_padl = g->il_padl; P.il_nb = g->il_nb;
+    P.fp = g->d_fp; P.rayt = g->d_rayt; P.angt = g->d_angt; P.order = g->d_order;
+    P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
+    P.NA = c.NA; P.nbuf = c.nbuf; P.CS = c.CS; P.rows_per_cta = c.rows_per_cta; P.ring_bytes = (int)c.ring_bytes; P.L = c.L;
+    P.need_cls[0] = ncls[0] > 0; P.need_cls[1] = ncls[1] > 0;
+    P.tma = c.tma;
+    for (int k = 0; k < 2; ++k) { P.spitch[k] = c.spitch[k]; P.nbox[k] = c.nbox[k]; P.bw[k] = c.bw[k]; }
+}
+
+// Packed-copy path (groups of 1 or 2 samples, whose 4/8-byte pixels are below the 16-byte granule of a tensor copy):
+// pack pass (producer fused in) + march over 1-D bulk copies
+int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
+                     int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes, cudaStream_t st,
+                     const FpPrologue *prologue)
+{
+    FpPrologue Q;
+    if (prologue) Q = *prologue; else { memset(&Q, 0, sizeof(Q)); }
+    // angles of each class inside the range
+    int ncls[2] = {0, 0};
+    for (int a = angle_lo; a < angle_hi; ++a) ncls[g->h_fp[a].cls]++;
+    MqConfig c = mq_choose(g, batch, std::max(ncls[0], ncls[1]));
+    if (c.smem > (size_t)g->smem_optin || !c.NSLOT) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
+    const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
+    if (!scratch || sp + c.scratch_bytes > (uintptr_t)scratch + scratch_bytes) {
+        scd_set_error("scd_fp: scratch too small (%zu bytes given, %zu needed; see scd_fp_scratch_bytes)",
+                      scratch_bytes, c.scratch_bytes + 128);
+        return SCD_E_WORKSPACE;
+    }
+    MqParams P;
+    mq_fill_params(g, c, P, sino, sino_il, batch, ncls);
+    P.img = img; P.packed = (float *)sp;
+
+    // ---- pack: image -> tile-ready layout (both orientations), producer fused in ----
+    {
+        if (c.groups > 65535) { scd_set_error("scd_fp: batch too large"); return SCD_E_INVALID; }
+        dim3 pg((std::max(g->n1, c.L.rows[1]) + PK_T - 1) / PK_T, (std::max(g->n0, c.L.rows[0]) + PK_T - 1) / PK_T, c.groups);
+#define PK_CASE(SS)                                                                                  \
+        if (c.SB == SS) {                                                                               \
+            if (Q.mode == 0) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<0, SS>, pg, dim3(256), 0, st, 0, P, Q));       \
+            else if (Q.mode == 1) SCD_CUDA(scd_launch_kernel(fp_packq_kernel<1, SS>, pg, dim3(256), 0, st, 0, P, Q));  \
+            else SCD_CUDA(scd_launch_kernel(fp_packq_kernel<2, SS>, pg, dim3(256), 0, st, 0, P, Q));                   \
+        }
+        PK_CASE(1) PK_CASE(2) PK_CASE(4) PK_CASE(8) PK_CASE(16)
+#undef PK_CASE
+        SCD_LAUNCH_CHECK("fp_packq_kernel");
+    }
+    CUtensorMap tms[2];
+    memset(tms, 0, sizeof(tms));
+    return mq_march(g, c, P, tms, angle_lo, angle_hi, st);
+}
+
+// Tensor-copy path: project a sample-interleaved image img_il[group][k0][k1][SB] (SB = scd_group_samples >= 4) --
+// one launch, no packed copy.  acc != nullptr: q = A img + beta * q_old (see MqParams).
+int scd_launch_fp_ilimg(const scd_geom *g, const float *img_il, float *sino, float *sino_il, int batch,
+                        int angle_lo, int angle_hi, cudaStream_t st, const FpAccumulate *acc)
+{
+    if (g && batch == 0) return 0;
+    if (!g || !img_il || (!sino && !sino_il)) { scd_set_error("scd_fp: null argument"); return SCD_E_INVALID; }
+    if (batch < 0 || angle_lo < 0 || angle_hi > g->n_angles || angle_lo > angle_hi) {
+        scd_set_error("scd_fp: bad batch/angle range (batch=%d, angles [%d,%d) of %d)", batch, angle_lo, angle_hi, g->n_angles);
+        return SCD_E_INVALID;
+    }
+    if (angle_lo == angle_hi) return 0;
+    if (!scd_il_image_ok(g, batch)) { scd_set_error("scd_fp: no tensor-copy path for this batch / image size"); return SCD_E_INVALID; }
+    if (((uintptr_t)img_il & 127) != 0) { scd_set_error("scd_fp: interleaved image must be 128-byte aligned"); return SCD_E_INVALID; }
+    int ncls[2] = {0, 0};
+    for (int a = angle_lo; a < angle_hi; ++a) ncls[g->h_fp[a].cls]++;
+    MqConfig c = mq_choose(g, batch, std::max(ncls[0], ncls[1]), true);
+    if (c.smem > (size_t)g->smem_optin || !c.NSLOT) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
+    MqParams P;
+    mq_fill_params(g, c, P, sino, sino_il, batch, ncls);
+    if (acc) {
+        P.acc_mode = 1;
+        P.rr_new_part = acc->rr_new_part; P.rr_new_n = acc->rr_new_n;
+        P.rr_old_part = acc->rr_old_part; P.rr_old_n = acc->rr_old_n; P.part_stride = acc->part_stride;
+        P.beta_out = acc->beta_out;
+    }
+    CUtensorMap tms[2];
+    int rc = mq_make_maps(g, img_il, c, tms);
+    if (rc) return rc;
+    return mq_march(g, c, P, tms, angle_lo, angle_hi, st);
+}
+
+// Whether batches of this size run on the tensor-copy path: groups of >= 4 samples (a pixel of the interleaved
+// image is then >= 16 bytes, the granule of a tensor copy) whose strip rows need at most 32 copies per strip
+// (one per lane of the producer warp)
+bool scd_il_image_ok(const scd_geom *g, int batch)
+{
+    if (!g || batch <= 0) return false;
+    if (g->tune_fp_source == 1) return false;          // tuning: force the packed-copy path
+    const int SB = scd_group_samples(g, batch);
+    if (SB < 4 || !mq_encoder()) return false;
+    int sp[2], nb[2], bw[2];
+    mq_tma_rows(g, SB, sp, nb, bw);
+    const int trmax = SB >= 16 ? 4 : 8;
+    return nb[0] * trmax <= 32 && nb[1] <= 32;
+}
+
+size_t scd_il_image_bytes(const scd_geom *g, int batch)
+{
+    if (!g || batch <= 0) return 0;
+    // the group size may be overridden by tuning: size for the worst case (a multiple of 16 samples)
+    return (size_t)((batch + 15) / 16) * 16 * g->n0 * g->n1 * 4;
 }
 
 // ------------------------------------------------------------- entry point ---
@@ -879,10 +1137,24 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, float *sino_
         return SCD_E_INVALID;
     }
     if (batch == 0 || angle_lo == angle_hi) return 0;
+    if (!(prologue && prologue->mode != 0) && scd_il_image_ok(g, batch)) {
+        // user-layout images: one interleaving pass (1 x the image, instead of the 2.06 x packed copy), then the
+        // tensor-copy march
+        const uintptr_t sp = ((uintptr_t)scratch + 127) & ~(uintptr_t)127;
+        const int SB = scd_group_samples(g, batch);
+        const size_t need = (size_t)((batch + SB - 1) / SB) * SB * g->n0 * g->n1 * 4;
+        if (!scratch || sp + need > (uintptr_t)scratch + scratch_bytes) {
+            scd_set_error("scd_fp: scratch too small (%zu bytes given, %zu needed; see scd_fp_scratch_bytes)", scratch_bytes, need + 128);
+            return SCD_E_WORKSPACE;
+        }
+        int rc = scd_launch_il_pack(g, img, (float *)sp, nullptr, nullptr, batch, st);
+        if (rc) return rc;
+        return scd_launch_fp_ilimg(g, (const float *)sp, sino, sino_il, batch, angle_lo, angle_hi, st, nullptr);
+    }
     return scd_launch_fp_v4(g, img, sino, sino_il, batch, angle_lo, angle_hi, scratch, scratch_bytes, st, prologue);
 }
 
 size_t scd_fp_scratch_need(const scd_geom *g, int batch)
 {
-    return scd_fp_scratch_need_v4(g, batch);
+    return std::max(scd_fp_scratch_need_v4(g, batch), scd_il_image_bytes(g, batch) + 256);
 }

@@ -84,6 +84,7 @@ extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
     g->x_min = d->x_min; g->y_min = d->y_min; g->dx = d->dx;
     g->s_min = d->s_min; g->ds = d->ds; g->adj_scale = d->adj_scale;
     g->device = dev;
+    { const char *e = getenv("SCD_FP_SOURCE"); if (e && !strcmp(e, "packed")) g->tune_fp_source = 1; }   // A/B runs
     { static std::atomic<unsigned long long> next_id{1}; g->id = next_id.fetch_add(1); }
     g->sm_count = prop.multiProcessorCount;
     g->smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -201,7 +202,7 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_nbuf")) g->tune_fp_nbuf = value;
     else if (!strcmp(key, "fp_cluster")) g->tune_fp_cluster = value;
     else if (!strcmp(key, "fp_plan")) g->tune_fp_plan = value;
-    else if (!strcmp(key, "fp_skip_pack")) g->tune_fp_skip_pack = value;
+    else if (!strcmp(key, "fp_source")) g->tune_fp_source = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
     else if (!strcmp(key, "bp_share")) g->tune_bp_share = value;
     else if (!strcmp(key, "bp_rows")) {

@@ -128,8 +128,9 @@ struct scd_geom {
     int     *h_order;
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
-    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan, tune_fp_skip_pack;
+    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan;
     int tune_bp_tile, tune_bp_share, tune_bp_rows;
+    int tune_fp_source;   // 1: force the packed-copy path of the projector (A/B runs, tests)
     // sample-interleaved sinogram rows (bp_tile.cu): il_padl zero bins, n_det bins, zero bins up to il_nb
     int il_padl, il_nb;
 };
@@ -154,6 +155,37 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, float *sino_
                   cudaStream_t st, const FpPrologue *prologue = nullptr);
 // samples interleaved per pixel / detector bin for this batch (1, 2, 4, 8 or 16)
 int scd_group_samples(const scd_geom *g, int batch);
+
+// ---- sample-interleaved images ("il image": [group][k0][k1][SB], SB = scd_group_samples(batch) >= 4) ----
+// The projector reads them with tensor copies (no packed copy); the CG vectors live in this layout for the whole solve.
+bool   scd_il_image_ok(const scd_geom *g, int batch);         // does this batch run on the tensor-copy path?
+size_t scd_il_image_bytes(const scd_geom *g, int batch);      // bytes of one il image (upper bound over the tuning)
+// recurrence of the CG solve carried by the projector's output phase: q = A img + beta * q_old,
+// beta[b] = sum(rr_new_part[b]) / sum(rr_old_part[b]); beta is also stored to beta_out[b] (may be NULL)
+struct FpAccumulate {
+    const float *rr_new_part; int rr_new_n; const float *rr_old_part; int rr_old_n; int part_stride;
+    float *beta_out;
+};
+int scd_launch_fp_ilimg(const scd_geom *g, const float *img_il, float *sino, float *sino_il, int batch,
+                        int angle_lo, int angle_hi, cudaStream_t st, const FpAccumulate *acc);
+// user layout -> il image for up to two arrays in one launch (b_user / b_il may be NULL)
+int scd_launch_il_pack(const scd_geom *g, const float *a_user, float *a_il, const float *b_user, float *b_il,
+                       int batch, cudaStream_t st);
+// il image -> user layout
+int scd_launch_il_unpack(const scd_geom *g, const float *a_il, float *a_user, int batch, cudaStream_t st);
+// Tweedie + rhs producing the CG start iterate and right-hand side in il layout (xhat0 also in user layout)
+int scd_launch_tweedie_il(const scd_geom *g, const float *x, const float *s, const float *atb, const float *t,
+                          const float *abar, int n_table, float gamma, float *xhat0_user, float *x_il, float *b_il,
+                          int batch, cudaStream_t st);
+// DDIM update reading the CG result in il layout, writing user layout
+int scd_launch_ddim_il(const scd_geom *g, const float *xh_il, const float *s, const float *eps, const float *t,
+                       const float *t_prev, const float *abar, int n_table, float eta, float eta2, float *out,
+                       int batch, cudaStream_t st);
+// alpha = rr/pd;  x += alpha p;  r -= alpha d;  per-block partials of ||r||^2 -- all vectors il images
+int scd_il_vec_blocks(const scd_geom *g, int batch);           // partials per sample written by the kernel below
+int scd_launch_cg_update_xr_il(const scd_geom *g, float *x, float *r, const float *p, const float *d,
+                               const float *rr_part, int rr_n, const float *pd_part, int pd_n, int part_stride,
+                               float *rr_new_part, int batch, cudaStream_t st);
 size_t scd_fp_scratch_need(const scd_geom *g, int batch);
 int scd_launch_fp_v4(const scd_geom *g, const float *img, float *sino, float *sino_il, int batch,
                      int angle_lo, int angle_hi, void *scratch, size_t scratch_bytes,
@@ -178,6 +210,15 @@ struct BpEpilogue {
     // of `out`; band_rows is a multiple of 32 (every tile lies inside one band).
     float *band_out[SCD_MAX_BANDS] = {};
     int n_bands = 0, band_rows = 0;
+    // Sample-interleaved images (il != 0): out, out2, add1, add2 are il images [group][k0][k1][SB] and every lane
+    // moves its V samples of a pixel with one vector access.
+    //   mode 0: as above.
+    //   mode 1 (direction step of CG, reference src/utils/cg.py:24-27,35-38):
+    //           p  = add1 + beta[b]*add2      (add1 = r, add2 = previous p; beta == NULL: p = add1)  -> out2
+    //           d  = p + c_acc*BP                                                                    -> out
+    //           dot_part: <p, d>
+    int il = 0, mode = 0;
+    const float *beta = nullptr;
 };
 // sino in user layout; scratch (>= scd_sino_il_bytes) receives the interleaved copy
 int scd_launch_bp(const scd_geom *g, const float *sino, float *out, int batch,

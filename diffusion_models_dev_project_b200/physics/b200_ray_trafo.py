@@ -303,6 +303,70 @@ class B200RayTrafo(BaseRayTrafo):
                                         float(addend_scale), _stream_ptr(buf.device)), 'scd_bp_il')
         return x
 
+    # ------------------------------------------- sample-interleaved images ---
+    def il_supported(self, batch: int, device) -> bool:
+        """Whether batches of this size have an interleaved-image form (>= 3 samples: groups of >= 4)."""
+        h = self._handle(torch.device(device))
+        return int(h._lib.scd_img_il_bytes(h.ptr, int(batch))) > 0
+
+    def _il_buffer(self, batch: int, device) -> Tensor:
+        h = self._handle(device)
+        n = int(h._lib.scd_img_il_bytes(h.ptr, batch))
+        if n == 0:
+            raise ValueError('batches of %d sample(s) have no interleaved-image form' % batch)
+        buf = torch.empty(n + 256, dtype=torch.uint8, device=h.device)
+        off = (-buf.data_ptr()) % 256
+        return buf[off:off + n]
+
+    def _img_il(self, x: Tensor) -> Tensor:
+        """``x`` as a sample-interleaved image (opaque 256-byte aligned byte buffer, scd_img_il_pack)."""
+        x = self._prep(x, self.im_shape, 'il image')
+        h = self._handle(x.device)
+        batch = int(np.prod(x.shape[:-2])) if x.dim() > 2 else 1
+        buf = self._il_buffer(batch, x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(h._lib.scd_img_il_pack(h.ptr, x.data_ptr(), buf.data_ptr(), batch, _stream_ptr(x.device)),
+                       'scd_img_il_pack')
+        return buf
+
+    def _img_from_il(self, buf: Tensor, lead) -> Tensor:
+        h = self._handle(buf.device)
+        batch = int(np.prod(lead)) if len(lead) else 1
+        x = torch.empty(*lead, *self.im_shape, dtype=torch.float32, device=buf.device)
+        with torch.cuda.device(buf.device):
+            _lib.check(h._lib.scd_img_il_unpack(h.ptr, buf.data_ptr(), x.data_ptr(), batch, _stream_ptr(buf.device)),
+                       'scd_img_il_unpack')
+        return x
+
+    def _fp_ilimg(self, img_il: Tensor, batch: int, angle_range=None) -> Tensor:
+        """A of an interleaved image -> interleaved sinogram: ONE launch of the projector (tensor copies straight
+        from the image, no packed copy).  Returns the cached sino_il buffer of this batch size."""
+        h = self._handle(img_il.device)
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        key = ('il', h.device.index, batch)
+        buf = self._work.get(key)
+        if buf is None:
+            buf = torch.empty(int(h._lib.scd_sino_il_buffer_bytes(h.ptr, batch)) + 256, dtype=torch.uint8, device=h.device)
+            self._cache_put(key, buf)
+        bp, _ = self._aligned(buf)
+        with torch.cuda.device(img_il.device):
+            _lib.check(h._lib.scd_fp_ilimg(h.ptr, img_il.data_ptr(), bp, batch, lo, hi, _stream_ptr(img_il.device)),
+                       'scd_fp_ilimg')
+        return buf
+
+    def _bp_ilimg(self, sino_il: Tensor, batch: int, scale: float, addend_il: Tensor = None, addend_scale: float = 0.0,
+                  angle_range=None, out_il: Tensor = None) -> Tensor:
+        """``scale * BP(sino_il) + addend_scale * addend_il`` as an interleaved image: ONE launch."""
+        h = self._handle(sino_il.device)
+        lo, hi = angle_range if angle_range is not None else (0, self.obs_shape[0])
+        out = out_il if out_il is not None else self._il_buffer(batch, sino_il.device)
+        sp, _ = self._aligned(sino_il)
+        with torch.cuda.device(sino_il.device):
+            _lib.check(h._lib.scd_bp_ilimg(h.ptr, sp, out.data_ptr(), batch, lo, hi, float(scale),
+                                           addend_il.data_ptr() if addend_il is not None else None, float(addend_scale),
+                                           _stream_ptr(sino_il.device)), 'scd_bp_ilimg')
+        return out
+
     def normal_apply(self, v: Tensor, gamma: float, angle_range=None, add_identity: bool = True,
                      out: Tensor = None) -> Tensor:
         """``v + gamma*A*(A v)``: the projector writes the sinogram in the layout the backprojector

@@ -69,8 +69,8 @@ int scd_geom_destroy(scd_geom_t *g);
 /* A: forward projection of angles [angle_lo, angle_hi) (rows outside that
  * range of `sino` are left untouched; sino always has n_angles rows).
  * `scratch` is a caller-owned device buffer of at least
- * scd_fp_scratch_bytes(g, batch) bytes: the projector first re-packs the images
- * into the layout its shared-memory strips are bulk-copied from.
+ * scd_fp_scratch_bytes(g, batch) bytes: the projector first interleaves the samples
+ * of a group per pixel (the layout its shared-memory strips are fetched from).
  * Replaces: SimpleTrafo.trafo -> ODL/ASTRA par_fp (src/physics/trafo.py:58). */
 size_t scd_fp_scratch_bytes(const scd_geom_t *g, int batch);
 int scd_fp(const scd_geom_t *g, const float *img, float *sino, int batch,
@@ -103,6 +103,25 @@ int scd_fp_il(const scd_geom_t *g, const float *img, float *sino_il, int batch,
 int scd_bp_il(const scd_geom_t *g, const float *sino_il, float *out, int batch,
               int angle_lo, int angle_hi, float c_acc, const float *addend, float c_add,
               void *stream);
+
+/* Sample-interleaved images ("il image": [group][n0][n1][samples of the group], 128-byte aligned, opaque like
+ * sino_il).  For batches of >= 3 samples the projector reads this layout directly through tensor copies
+ * (cp.async.bulk.tensor: no packed copy of the image) and the backprojector writes it with one 16-byte
+ * store per lane; scd_cg / scd_dds_step keep x, r, p, d in it for the whole solve.  A caller that iterates
+ * with A / A* itself can do the same:
+ *   scd_img_il_bytes   bytes of one il image for `batch` samples; 0 if this batch size has no il form
+ *                      (1 or 2 samples: pixels below the 16-byte granule of a tensor copy)
+ *   scd_img_il_pack / scd_img_il_unpack   [batch][n0][n1] <-> il image
+ *   scd_fp_ilimg       sino_il = A(img_il)                                   -- ONE launch (fp_march)
+ *   scd_bp_ilimg       out_il = c_acc * BP(sino_il) + c_add * addend_il      -- ONE launch (bp_tile)
+ * Replaces: the same call sites as scd_fp_il / scd_bp_il.                                      */
+size_t scd_img_il_bytes(const scd_geom_t *g, int batch);
+int scd_img_il_pack(const scd_geom_t *g, const float *img, float *img_il, int batch, void *stream);
+int scd_img_il_unpack(const scd_geom_t *g, const float *img_il, float *img, int batch, void *stream);
+int scd_fp_ilimg(const scd_geom_t *g, const float *img_il, float *sino_il, int batch,
+                 int angle_lo, int angle_hi, void *stream);
+int scd_bp_ilimg(const scd_geom_t *g, const float *sino_il, float *out_il, int batch,
+                 int angle_lo, int angle_hi, float c_acc, const float *addend_il, float c_add, void *stream);
 
 /* Bytes of scratch scd_cg / scd_dds_step need for `batch` samples.           */
 size_t scd_cg_workspace_bytes(const scd_geom_t *g, int batch);
@@ -216,7 +235,8 @@ int64_t scd_launch_count(void);
 void    scd_launch_count_reset(void);
 /* Override launch heuristics (tuning / tests).  key is one of
  * "fp_samples" (samples interleaved per pixel/bin: 1,2,4,8,16), "fp_angles", "fp_rows",
- * "fp_threads", "fp_nbuf", "fp_cluster", "fp_plan", "fp_skip_pack", "bp_tile", "bp_share" (1 = plain
+ * "fp_threads", "fp_nbuf", "fp_cluster", "fp_plan", "fp_source" (1 = packed copy + 1-D bulk copies for every
+ * batch size instead of tensor copies from the interleaved image), "bp_tile", "bp_share" (1 = plain
  * march, no tap sharing between the pixels of a column pair), "bp_rows" (rows in use per tile; 1 = always the
  * full tile); value 0
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */

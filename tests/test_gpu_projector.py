@@ -80,7 +80,8 @@ def test_fp_bp_other_shapes(im_shape, num_angles):
                                   dict(fp_samples=1, bp_tile=32), dict(fp_samples=2, bp_tile=16), dict(fp_samples=4, bp_tile=32),
                                   dict(fp_samples=8, bp_tile=32), dict(fp_samples=8, bp_tile=16), dict(fp_samples=8, bp_tile=8), dict(fp_samples=16, bp_tile=8), dict(fp_samples=16),
                                   dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_threads=768), dict(fp_samples=8, fp_angles=3, fp_rows=8, fp_threads=768, fp_cluster=2), dict(fp_samples=4, fp_threads=768),
-                                  dict(fp_samples=4, bp_tile=16), dict(fp_samples=2, bp_tile=32)])
+                                  dict(fp_samples=4, bp_tile=16), dict(fp_samples=2, bp_tile=32),
+                                  dict(fp_samples=4, fp_source=1), dict(fp_samples=8, fp_source=1, fp_cluster=2), dict(fp_samples=16, fp_source=1, fp_rows=2)])
 def test_tuning_variants_agree(tune):
     """Every template instantiation (samples per thread, rays per thread, tile shape) computes the same thing."""
     geom = O.OracleGeometry((96, 96), 20)
@@ -318,3 +319,34 @@ def test_host_buffer_entry_points():
     assert rel_l2(z, O.bp(geom, y)) < TOL
     assert h._lib.scd_fp(h.ptr, None, None, 1, 0, 10, None, 0, None) == _lib.SCD_E_INVALID
     assert 'null' in _lib.last_error()
+
+
+@pytest.mark.parametrize('im_shape,num_angles,batch', [((256, 256), 60, 8), ((256, 256), 60, 40), ((96, 70), 13, 3),
+                                                        ((501, 501), 24, 5), ((64, 64), 9, 16), ((33, 17), 5, 4)])
+def test_interleaved_image_path(im_shape, num_angles, batch):
+    """Sample-interleaved images (batches >= 3): pack / unpack round trip, A through tensor copies from the image
+    (no packed copy), A* writing the interleaved layout -- against the oracle and against the packed-copy path."""
+    geom = O.OracleGeometry(im_shape, num_angles)
+    rt = _rt(im_shape, num_angles)
+    assert rt.il_supported(batch, 'cuda') and not rt.il_supported(2, 'cuda') and not rt.il_supported(1, 'cuda')
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.random((batch, 1, *im_shape), dtype=np.float32)).cuda()
+    x_il = rt._img_il(x)
+    assert torch.equal(rt._img_from_il(x_il, x.shape[:-2]), x)
+    n = min(batch, 3)
+    y_ref = O.fp(geom, x[:n].cpu().numpy())
+    y = rt(x)
+    assert rel_l2(y[:n].cpu().numpy(), y_ref) < TOL
+    assert rel_l2(y[-1].cpu().numpy(), O.fp(geom, x[-1].cpu().numpy())) < TOL
+    rt.set_tuning('cuda', fp_source=1)
+    y_packed = rt(x)
+    rt.set_tuning('cuda', fp_source=0)
+    assert rel_l2(y.cpu().numpy(), y_packed.cpu().numpy()) < 1e-6
+    q = rt._fp_ilimg(x_il, batch)
+    z = rt._img_from_il(rt._bp_ilimg(q, batch, rt.adj_scale), x.shape[:-2])
+    assert rel_l2(z[:n].cpu().numpy(), O.bp(geom, y_ref)) < TOL
+    assert rel_l2(z.cpu().numpy(), rt.trafo_adjoint(y).cpu().numpy()) < 1e-6
+    z2 = rt._img_from_il(rt._bp_ilimg(q, batch, 0.5 * rt.adj_scale, addend_il=x_il, addend_scale=2.0), x.shape[:-2])
+    assert rel_l2(z2.cpu().numpy(), (0.5 * z + 2.0 * x).cpu().numpy()) < 1e-6
+    with pytest.raises(ValueError):
+        rt._img_il(x[:2])

@@ -42,7 +42,8 @@ def test_library_contains_sm100a_code_with_bulk_copies():
     out = subprocess.run(['cuobjdump', '-lelf', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in out
     sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert 'UBLKCP' in sass          # cp.async.bulk (TMA unit) feeding fp_joseph
+    assert 'UBLKCP' in sass          # cp.async.bulk (TMA unit): packed strips / sinogram segments
+    assert 'UTMALDG' in sass         # cp.async.bulk.tensor: strips gathered from the interleaved image
     assert 'SYNCS' in sass           # mbarrier
 
 

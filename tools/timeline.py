@@ -14,9 +14,11 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from diffusion_models_dev_project_b200 import build as _build  # noqa: E402
-os.environ['SCD_B200_LIB'] = _build.build(debug=True)
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ['SCD_B200_LIB'] = os.path.join(_ROOT, 'diffusion_models_dev_project_b200', '_lib', 'libscd_b200_dbg.so')   # before the import
 import diffusion_models_dev_project_b200 as pkg  # noqa: E402
+from diffusion_models_dev_project_b200 import build as _build  # noqa: E402
+assert _build.build(debug=True) == os.environ['SCD_B200_LIB']
 from diffusion_models_dev_project_b200 import _lib  # noqa: E402
 
 NAMES = {'fp': ['cta start', 'tables done', 'predecessor complete', 'first strip landed', 'march done',
@@ -33,6 +35,7 @@ def main():
     ap.add_argument('--angles', type=int, default=60)
     ap.add_argument('--set', default='')
     ap.add_argument('--dump', default='', help='write the raw stamps (ns, [CTA, 8]) to this .npy file')
+    ap.add_argument('--mod', type=int, default=0, help='also print the median CTA duration per (CTA index mod MOD): with MOD = units per group of fp_march it separates the angle classes')
     a = ap.parse_args()
     dev = torch.device('cuda')
     rt = pkg.B200RayTrafo((a.im, a.im), a.angles)
@@ -71,6 +74,11 @@ def main():
         print('  %-22s min %7.2f  med %7.2f  max %7.2f us' % (name, rel.min(), np.median(rel), rel.max()))
     dur = (s[:, [c for c in range(8) if (s[:, c] > 0).all()][-1]] - s[:, 0]) / 1e3
     print('  per-CTA duration       min %7.2f  med %7.2f  max %7.2f us' % (dur.min(), np.median(dur), dur.max()))
+    if a.mod:
+        idx = np.arange(len(dur))
+        march = (s[:, 4] - s[:, 3]) / 1e3
+        print('  median duration / march phase per CTA index mod %d:' % a.mod)
+        print('   ', ' '.join('%d:%.0f/%.0f' % (m, np.median(dur[idx % a.mod == m]), np.median(march[idx % a.mod == m])) for m in range(a.mod)))
 
 
 if __name__ == '__main__':
