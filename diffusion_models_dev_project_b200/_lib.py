@@ -56,6 +56,11 @@ SIGNATURES = {
     "scd_tv_blocks": (C.c_int, [C.c_int, C.c_int]),
     "scd_tv_loss": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scd_tv_grad": (C.c_int, [_F, _F, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scd_adapt_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "scd_adapt_fwd": (C.c_int, [C.c_void_p, _F, _F, _F, _F, _F, _F, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double,
+                                _F, _F, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "scd_adapt_bwd": (C.c_int, [C.c_void_p, _F, _F, _F, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                _F, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "scd_ramp_filter": (C.c_int, [C.c_void_p, _F, _F, C.c_int, C.c_void_p]),
     "scd_bp_banded": (C.c_int, [C.c_void_p, _F, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                 C.c_void_p, C.c_size_t, C.c_void_p]),

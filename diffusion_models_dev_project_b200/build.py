@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libscd_b200.so")
 DEBUG_LIB_PATH = os.path.join(LIB_DIR, "libscd_b200_dbg.so")
-SOURCES = ["geometry.cu", "fp_march.cu", "bp_tile.cu", "vec_ops.cu", "il_ops.cu", "loss_ops.cu", "fbp_filter.cu", "cg_solver.cu", "peer_reduce.cu"]
+SOURCES = ["geometry.cu", "fp_march.cu", "bp_tile.cu", "vec_ops.cu", "il_ops.cu", "loss_ops.cu", "adapt_ops.cu", "fbp_filter.cu", "cg_solver.cu", "peer_reduce.cu"]
 HEADERS = [os.path.join(CSRC, "scd_internal.cuh"), os.path.join(ROOT, "include", "scd_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -37,6 +37,12 @@ unsigned long long *scd_debug_stamps() { return g_stamps; }
 extern "C" void scd_debug_set_stamps(void *device_buffer) { g_stamps = (unsigned long long *)device_buffer; }
 #endif
 
+bool scd_sync_launches()
+{
+    static const bool on = getenv("SCD_SYNC_LAUNCHES") != nullptr;
+    return on;
+}
+
 bool scd_pdl_enabled()
 {
     static const bool on = getenv("SCD_NO_PDL") == nullptr;

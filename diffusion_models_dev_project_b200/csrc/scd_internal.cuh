@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdio.h>
 #include "scd_b200.h"
 
 // ---------------------------------------------------------------- errors ---
@@ -16,9 +17,13 @@ void scd_count_launch(int n = 1);
         if (e__ != cudaSuccess) return scd_cuda_fail(e__, #call);             \
     } while (0)
 
+// SCD_SYNC_LAUNCHES=1 in the environment: synchronise the device after every launch of the library and report
+// the first kernel that faults by name (debugging aid; breaks graph capture and every overlap)
+bool scd_sync_launches();
 #define SCD_LAUNCH_CHECK(name)                                                \
     do {                                                                      \
         cudaError_t e__ = cudaGetLastError();                                 \
+        if (e__ == cudaSuccess && scd_sync_launches()) { e__ = cudaDeviceSynchronize(); fprintf(stderr, "[scd] %s -> %d\n", name, (int)e__); } \
         if (e__ != cudaSuccess) return scd_cuda_fail(e__, name);              \
         scd_count_launch();                                                   \
     } while (0)

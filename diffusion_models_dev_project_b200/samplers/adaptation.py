@@ -70,6 +70,99 @@ def adaptation_loss(x, observation, ray_trafo, tv_penalty: float):
     return torch.mean((ray_trafo(x) - observation).pow(2)) + float(tv_penalty) * tv_loss(x)
 
 
+class AdaptationLoss:
+    """The loss closure of ``get_standard_adapted_sampler`` (reference src/utils/exp_utils.py:256-257) as an
+    object, so that :func:`..samplers.utils._adapt` can recognise it and evaluate Tweedie -> data consistency ->
+    loss and the whole backward sweep as two library calls (``scd_adapt_fwd`` / ``scd_adapt_bwd``).  Calling it
+    evaluates the loss at ``x`` like the reference's lambda."""
+
+    def __init__(self, observation, ray_trafo, tv_penalty: float):
+        self.observation, self.ray_trafo, self.tv_penalty = observation, ray_trafo, float(tv_penalty)
+
+    def __call__(self, x):
+        return adaptation_loss(x, self.observation, self.ray_trafo, self.tv_penalty)
+
+
+_DC_CODES = {'cg': 0, 'dc': 1, 'gd': 1, 'none': 2}
+
+
+class _AdaptObjectiveFn(torch.autograd.Function):
+    """``loss(s) = AdaptationLoss(dc(apTweedy(s, x)))`` with ``dc`` = CG(n_iter) | one gradient step | identity:
+    one library call forward, one backward (``csrc/adapt_ops.cu``).  The reverse sweep differentiates the unrolled
+    CG recurrences exactly, as autograd does for the reference (src/samplers/utils.py:241-260)."""
+
+    @staticmethod
+    def forward(ctx, s, x, t, atb, y, rt, abar, gamma, n_iter, dc_code, lam):
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.load()
+        x = rt._prep(x, rt.im_shape, 'adapt x')
+        s = rt._prep(s, rt.im_shape, 'adapt s')
+        if s.shape != x.shape:
+            raise ValueError('adapt: s %r and x %r differ in shape' % (tuple(s.shape), tuple(x.shape)))
+        dev = x.device
+        h = rt._handle(dev)
+        batch = int(x.numel() // (rt.im_shape[0] * rt.im_shape[1]))
+        atb = rt._prep(atb.to(dev).expand_as(x), rt.im_shape, 'adapt rhs') if atb is not None else None
+        y = rt._prep(y.to(device=dev, dtype=torch.float32).expand(*x.shape[:-2], *rt.obs_shape), rt.obs_shape, 'adapt y')
+        t = t.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
+        if t.numel() != batch:
+            raise ValueError('adapt: one time step per sample expected')
+        n_work = int(lib.scd_adapt_workspace_bytes(h.ptr, batch, int(n_iter)))
+        work = torch.empty(n_work + 256, dtype=torch.uint8, device=dev)      # carries the saved vectors to backward
+        wp = work.data_ptr() + (-work.data_ptr()) % 256
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(lib.scd_adapt_fwd(h.ptr, x.data_ptr(), s.data_ptr(), atb.data_ptr() if atb is not None else None,
+                                         y.data_ptr(), t.data_ptr(), abar.data_ptr(), int(abar.numel()), float(gamma),
+                                         int(n_iter), int(dc_code), float(lam), loss.data_ptr(), None, batch, wp, n_work,
+                                         stream), 'scd_adapt_fwd')
+        ctx.rt, ctx.work, ctx.wp, ctx.n_work, ctx.batch = rt, work, wp, n_work, batch
+        ctx.t, ctx.abar = t, abar
+        ctx.args = (float(gamma), int(n_iter), int(dc_code), float(lam))
+        ctx.shape = s.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        import ctypes as C
+        from .. import _lib
+        lib = _lib.load()
+        rt = ctx.rt
+        dev = ctx.t.device
+        h = rt._handle(dev)
+        gamma, n_iter, dc_code, lam = ctx.args
+        grad_s = torch.empty(ctx.shape, dtype=torch.float32, device=dev)
+        g = g.to(device=dev, dtype=torch.float32).contiguous()
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            _lib.check(lib.scd_adapt_bwd(h.ptr, g.data_ptr(), ctx.t.data_ptr(), ctx.abar.data_ptr(), int(ctx.abar.numel()),
+                                         gamma, n_iter, dc_code, lam, rt.adj_scale / rt.geometry.range_weight,
+                                         grad_s.data_ptr(), ctx.batch, ctx.wp, ctx.n_work, stream), 'scd_adapt_bwd')
+        ctx.work = None
+        return (grad_s,) + (None,) * 10
+
+
+def adapt_objective(s, x, time_step, rhs, loss_fn: 'AdaptationLoss', sde, gamma: float, n_iter: int, dc_type: str):
+    """Fused SCD adaptation objective, or ``None`` when the fused path does not apply (then the caller evaluates
+    the reference's tensor expression).  Applies to: :class:`AdaptationLoss` on a :class:`B200RayTrafo`, DDPM
+    schedule, CUDA fp32, 4-D single-channel tensors, ``s`` requiring grad and nothing else."""
+    from ..physics.b200_ray_trafo import B200RayTrafo
+    from ..utils.sde import DDPM
+    if not isinstance(loss_fn, AdaptationLoss) or not isinstance(loss_fn.ray_trafo, B200RayTrafo) or not isinstance(sde, DDPM):
+        return None
+    if dc_type not in _DC_CODES or not (s.is_cuda and s.dtype == torch.float32 and x.dtype == torch.float32):
+        return None
+    if x.requires_grad or (rhs is not None and rhs.requires_grad) or loss_fn.observation.requires_grad:
+        return None
+    if s.dim() != 4 or s.shape[1] != 1:
+        return None
+    return _AdaptObjectiveFn.apply(s, x, time_step, rhs, loss_fn.observation, loss_fn.ray_trafo,
+                                   sde.alpha_bar_table(x.device), float(gamma), int(n_iter), _DC_CODES[dc_type],
+                                   loss_fn.tv_penalty)
+
+
 def _score_model_adpt(score: nn.Module, impl: str = 'full', adpt_kwargs: Optional[Dict] = None,
                       verbose: bool = True, inject_fn=None) -> None:
     """Select the trainable parameters of the score model (reference :14-52).

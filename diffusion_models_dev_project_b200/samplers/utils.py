@@ -13,12 +13,14 @@ adaptation) or the schedule is VE/VP, the same formulas run as tensor
 operations, with A / A* still executed by the CUDA projector kernels through
 their autograd Functions.
 """
+import os
 from typing import Dict, Optional, Tuple, Union
 
 import torch
 from torch import Tensor
 
 from .. import fused
+from .adaptation import adapt_objective
 from ..physics.b200_ray_trafo import B200RayTrafo, NormalOp
 from ..utils.cg import cg
 from ..utils.sde import SDE, VESDE, VPSDE, DDPM, _SCORE_PRED_CLASSES
@@ -155,6 +157,14 @@ def _adapt(x: Tensor, score, sde: SDE, ray_trafo, loss_fn, time_step: Tensor, rh
     for _ in range(num_steps):
         optim.zero_grad()
         s = score(x, time_step)
+        # Tweedie -> data consistency -> loss and its whole backward sweep as two library calls when the loss is the
+        # standard adaptation loss on the CUDA operator (same arithmetic as the tensor path below)
+        loss = adapt_objective(s, x, time_step, rhs, loss_fn, sde, gamma, n_iter, dc_type) \
+            if os.environ.get('SCD_ADAPT_UNFUSED') != '1' else None
+        if loss is not None:
+            loss.backward()
+            optim.step()
+            continue
         xhat0 = apTweedy(s=s, x=x, sde=sde, time_step=time_step)
         if dc_type == "cg":
             xhat = cg(op=op, x=xhat0, rhs=xhat0 + gamma * rhs, n_iter=n_iter)

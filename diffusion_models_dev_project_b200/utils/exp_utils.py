@@ -16,7 +16,7 @@ import torch
 from .sde import VESDE, VPSDE, DDPM, _EPSILON_PRED_CLASSES
 from ..physics import B200RayTrafo, simulate
 from ..samplers import (BaseSampler, decomposed_diffusion_sampling_sde_predictor,
-                        adapted_ddim_sde_predictor, tv_loss, adaptation_loss, _adapt, _score_model_adpt,
+                        adapted_ddim_sde_predictor, tv_loss, adaptation_loss, AdaptationLoss, _adapt, _score_model_adpt,
                         Euler_Maruyama_sde_predictor, Ancestral_Sampling)
 
 
@@ -117,8 +117,7 @@ def get_standard_adapted_sampler(args, config, score, sde, ray_trafo, observatio
         adpt_kwargs = {'include_blocks': args.lora_include_blocks, 'r': int(args.lora_rank)}
     _score_model_adpt(score, impl=args.adaptation, adpt_kwargs=adpt_kwargs, inject_fn=lora_inject_fn)
 
-    def loss_fn(x):
-        return adaptation_loss(x, observation, ray_trafo, float(args.tv_penalty))
+    loss_fn = AdaptationLoss(observation, ray_trafo, float(args.tv_penalty))     # callable: loss_fn(x=...)
 
     adapt_fn = functools.partial(_adapt, score=score, sde=sde, loss_fn=loss_fn,
                                  num_steps=int(args.num_optim_step), lr=float(args.lr))

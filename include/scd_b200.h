@@ -180,6 +180,27 @@ int scd_tv_blocks(int n0, int n1);
 int scd_tv_loss(const float *x, float *part, int images, int n0, int n1, void *stream);
 int scd_tv_grad(const float *x, float *grad, int images, int n0, int n1, void *stream);
 
+/* The adaptation objective of SCD as two calls (forward, and the complete reverse sweep): per Adam step
+ * `_adapt` (src/samplers/utils.py:241-260) evaluates
+ *     xhat0 = apTweedy(s, x);  xhat = cg(op, xhat0, xhat0 + gamma*atb, n_iter)  [dc_type 0; 1: one gradient
+ *     step xhat0 - gamma A*(A xhat0) + gamma atb; 2: xhat = xhat0];  loss = mean((A xhat - y)^2) + tv_lambda*tv(xhat)
+ * and differentiates it with respect to the score output s (autograd through the unrolled CG iterations).
+ *   scd_adapt_fwd : loss[0] (device scalar), optionally xhat; keeps what the sweep needs in `work`
+ *   scd_adapt_bwd : grad_s = d(grad_loss[0] * loss)/d s  (grad_loss: device scalar or NULL = 1), from the
+ *                   SAME `work` buffer, untouched since the forward call.  trafo_grad_scale is the factor between
+ *                   the gradient of <g, A x> w.r.t. x and the plain backprojection sum: adj_scale/c_w under ODL's
+ *                   pairing (c_w = dphi*ds/dx^2).
+ * `work`: scd_adapt_workspace_bytes(g, batch, n_iter) bytes, 256-byte aligned.  y: [batch][n_angles][n_det].
+ * Nothing is allocated, synchronised or read back: both calls can be captured in a CUDA graph.            */
+size_t scd_adapt_workspace_bytes(const scd_geom_t *g, int batch, int n_iter);
+int scd_adapt_fwd(const scd_geom_t *g, const float *x, const float *s, const float *atb, const float *y,
+                  const float *t, const float *abar, int n_table, double gamma, int n_iter, int dc_type,
+                  double tv_lambda, float *loss, float *xhat_out, int batch, void *work, size_t work_bytes,
+                  void *stream);
+int scd_adapt_bwd(const scd_geom_t *g, const float *grad_loss, const float *t, const float *abar, int n_table,
+                  double gamma, int n_iter, int dc_type, double tv_lambda, double trafo_grad_scale,
+                  float *grad_s, int batch, void *work, size_t work_bytes, void *stream);
+
 /* Ramp filter of the filtered back-projection: every sinogram row is convolved along the detector
  * axis with the band-limited ramp (Kak & Slaney / the "ramp" Fourier filter of the reference's recipe)
  * and divided by the detector cell size:

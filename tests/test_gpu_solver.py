@@ -378,3 +378,46 @@ def test_workspace_validation():
     rc = h._lib.scd_cg(h.ptr, x.data_ptr(), x.data_ptr(), 0.1, 1, 1, w.data_ptr(), 1024, None)
     assert rc == _lib.SCD_E_WORKSPACE
     assert int(h._lib.scd_cg_workspace_bytes(h.ptr, 1)) > 5 * 32 * 32 * 4
+
+
+@pytest.mark.parametrize('dc_type,n_iter', [('cg', 1), ('cg', 3), ('cg', 0), ('dc', 1), ('none', 1)])
+@pytest.mark.parametrize('batch', [1, 2, 5])
+def test_fused_adaptation_objective_matches_the_tensor_path(dc_type, n_iter, batch):
+    """scd_adapt_fwd / scd_adapt_bwd (Tweedie -> CG | gradient step | none -> loss, and the hand-written reverse
+    sweep) against the tensor path: apTweedy, the differentiable cg, adaptation_loss, differentiated by autograd --
+    what `_adapt` evaluates per Adam step (reference src/samplers/utils.py:241-260)."""
+    pkg = _pkg()
+    from diffusion_models_dev_project_b200.samplers.adaptation import AdaptationLoss, adapt_objective
+    rt = pkg.B200RayTrafo((64, 64), 16)
+    sde = pkg.DDPM()
+    gen = torch.Generator(device='cuda').manual_seed(17)
+    gt = torch.rand(batch, 1, 64, 64, device='cuda', generator=gen)
+    gt = torch.nn.functional.avg_pool2d(gt, 5, 1, 2)
+    y = rt(gt) + 0.01 * torch.randn(batch, 1, *rt.obs_shape, device='cuda', generator=gen)
+    rhs = rt.trafo_adjoint(y)
+    t = torch.ones(batch, device='cuda') * 300.
+    ab = sde.alpha_bar_table('cuda')[301]
+    x = ab.sqrt() * gt + (1 - ab).sqrt() * torch.randn(batch, 1, 64, 64, device='cuda', generator=gen)
+    s0 = torch.randn(batch, 1, 64, 64, device='cuda', generator=gen)
+    gamma, lam = 0.05, 1e-3
+    loss_fn = AdaptationLoss(y, rt, lam)
+
+    sa = s0.clone().requires_grad_(True)
+    la = adapt_objective(sa, x, t, rhs, loss_fn, sde, gamma, n_iter, dc_type)
+    assert la is not None and la.dim() == 0
+    (3.0 * la).backward()
+
+    sb = s0.clone().requires_grad_(True)
+    xhat0 = pkg.apTweedy(s=sb, x=x, sde=sde, time_step=t)
+    if dc_type == 'cg':
+        xhat = pkg.cg(op=rt.normal_op(gamma), x=xhat0, rhs=xhat0 + gamma * rhs, n_iter=n_iter)
+    elif dc_type == 'dc':
+        xhat = xhat0 - gamma * rt.trafo_adjoint(rt(xhat0)) + gamma * rhs
+    else:
+        xhat = xhat0
+    lb = loss_fn(x=xhat)
+    (3.0 * lb).backward()
+    assert abs(float(la) - float(lb)) / abs(float(lb)) < 1e-5, (float(la), float(lb))
+    assert rel_l2(sa.grad.cpu().numpy(), sb.grad.cpu().numpy()) < 1e-4
+    # no fused path for other losses / operators: the caller falls back to the tensor expression
+    assert adapt_objective(sa, x, t, rhs, lambda x: x.sum(), sde, gamma, n_iter, dc_type) is None
