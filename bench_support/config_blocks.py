@@ -219,9 +219,17 @@ def adapted_block(dev, world, rank, steps=2, warm=1, full_unet=True):
         path = pkg.get_standard_adapted_sampler(args=a2, config=config, score=AdaptableScore().to(dev), sde=sde,
                                                 ray_trafo=rt, observation=y, device=dev)
         ms_path, launches, ok1 = time_steps(path)
+        # the same with one Adam step (score model, scd_adapt_fwd / scd_adapt_bwd, optimizer) captured in a CUDA graph
+        a3 = copy.copy(a2)
+        a3.adapt_cuda_graph = True
+        pathg = pkg.get_standard_adapted_sampler(args=a3, config=config, score=AdaptableScore().to(dev), sde=sde,
+                                                 ray_trafo=rt, observation=y, device=dev)
+        ms_graph, _, ok3 = time_steps(pathg)
+        ok1 = ok1 and ok3
         out = {'workload': 'SCD adapted sampling 256x256, 60 angles, batch 1 per GPU, 50 reverse steps per sample, '
                            '10 Adam steps per reverse step, LoRA rank 4, CG(1), tv 1e-6, eta 0.85',
-               'ms_per_reverse_step_path_only': ms_path, 'library_launches_per_reverse_step': launches,
+               'ms_per_reverse_step_path_only': ms_path, 'ms_per_reverse_step_path_only_cuda_graph': ms_graph,
+               'library_launches_per_reverse_step': launches,
                'finite': ok1}
         if full_unet:
             torch.manual_seed(0)

@@ -13,7 +13,7 @@
 #include <atomic>
 
 static thread_local char    g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};     // process-wide: autograd runs backward passes on its own threads
 
 void scd_set_error(const char *fmt, ...)
 {
@@ -29,7 +29,7 @@ int scd_cuda_fail(cudaError_t e, const char *what)
     return -(int)e;
 }
 
-void scd_count_launch(int n) { g_launches += n; }
+void scd_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #ifdef SCD_DEBUG_STAMPS
 static unsigned long long *g_stamps = nullptr;
@@ -51,8 +51,8 @@ bool scd_pdl_enabled()
 
 extern "C" const char *scd_last_error_string(void) { return g_err; }
 extern "C" const char *scd_version(void) { return "scd_b200 0.1 (sm_100a)"; }
-extern "C" int64_t scd_launch_count(void) { return g_launches; }
-extern "C" void scd_launch_count_reset(void) { g_launches = 0; }
+extern "C" int64_t scd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void scd_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
 
 extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
 {

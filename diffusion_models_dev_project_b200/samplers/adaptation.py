@@ -144,19 +144,24 @@ class _AdaptObjectiveFn(torch.autograd.Function):
         return (grad_s,) + (None,) * 10
 
 
-def adapt_objective(s, x, time_step, rhs, loss_fn: 'AdaptationLoss', sde, gamma: float, n_iter: int, dc_type: str):
-    """Fused SCD adaptation objective, or ``None`` when the fused path does not apply (then the caller evaluates
-    the reference's tensor expression).  Applies to: :class:`AdaptationLoss` on a :class:`B200RayTrafo`, DDPM
-    schedule, CUDA fp32, 4-D single-channel tensors, ``s`` requiring grad and nothing else."""
+def adapt_objective_applies(x, rhs, loss_fn, sde, dc_type: str) -> bool:
+    """Whether the fused objective covers this call: :class:`AdaptationLoss` on a :class:`B200RayTrafo`, DDPM
+    schedule, CUDA fp32, 4-D single-channel tensors, only the score output requiring grad."""
     from ..physics.b200_ray_trafo import B200RayTrafo
     from ..utils.sde import DDPM
     if not isinstance(loss_fn, AdaptationLoss) or not isinstance(loss_fn.ray_trafo, B200RayTrafo) or not isinstance(sde, DDPM):
-        return None
-    if dc_type not in _DC_CODES or not (s.is_cuda and s.dtype == torch.float32 and x.dtype == torch.float32):
-        return None
+        return False
+    if dc_type not in _DC_CODES or not (x.is_cuda and x.dtype == torch.float32):
+        return False
     if x.requires_grad or (rhs is not None and rhs.requires_grad) or loss_fn.observation.requires_grad:
-        return None
-    if s.dim() != 4 or s.shape[1] != 1:
+        return False
+    return x.dim() == 4 and x.shape[1] == 1
+
+
+def adapt_objective(s, x, time_step, rhs, loss_fn: 'AdaptationLoss', sde, gamma: float, n_iter: int, dc_type: str):
+    """Fused SCD adaptation objective, or ``None`` when the fused path does not apply (then the caller evaluates
+    the reference's tensor expression)."""
+    if not adapt_objective_applies(x, rhs, loss_fn, sde, dc_type) or s.shape != x.shape or s.dtype != torch.float32:
         return None
     return _AdaptObjectiveFn.apply(s, x, time_step, rhs, loss_fn.observation, loss_fn.ray_trafo,
                                    sde.alpha_bar_table(x.device), float(gamma), int(n_iter), _DC_CODES[dc_type],

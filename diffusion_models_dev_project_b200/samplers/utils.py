@@ -20,7 +20,7 @@ import torch
 from torch import Tensor
 
 from .. import fused
-from .adaptation import adapt_objective
+from .adaptation import adapt_objective, adapt_objective_applies
 from ..physics.b200_ray_trafo import B200RayTrafo, NormalOp
 from ..utils.cg import cg
 from ..utils.sde import SDE, VESDE, VPSDE, DDPM, _SCORE_PRED_CLASSES
@@ -143,16 +143,87 @@ def _has_lora_active(score):
     return (mods[0].scale != 0) if mods else None
 
 
+class _AdaptGraph:
+    """One Adam step of :func:`_adapt` -- score call, fused adaptation objective (``scd_adapt_fwd`` /
+    ``scd_adapt_bwd``), backward through the score model, optimizer step -- captured once in a CUDA graph and
+    replayed ``num_steps`` times per reverse step.  The reference builds a fresh ``Adam`` for every reverse step
+    (src/samplers/utils.py:240); the same effect is obtained by zeroing the moments and the step counter of the
+    captured (``capturable=True``) optimizer before the replays.  Inputs live in static buffers."""
+
+    def __init__(self, score, sde, loss_fn, x, time_step, rhs, lr, gamma, n_iter, dc_type):
+        self.key = self.make_key(loss_fn, x, rhs, lr, gamma, n_iter, dc_type)
+        self.x, self.t = x.detach().clone(), time_step.detach().clone()
+        self.rhs = rhs.detach().clone() if rhs is not None else None
+        params = list(score.parameters())
+        self.optim = torch.optim.Adam(params, lr=lr, capturable=True)
+
+        def one_step():
+            s = score(self.x, self.t)
+            loss = adapt_objective(s, self.x, self.t, self.rhs, loss_fn, sde, gamma, n_iter, dc_type)
+            loss.backward()
+            self.optim.step()
+        # warm-up on a side stream (lazy optimizer state, library handles, kernel attributes), then undo it
+        saved = [p.detach().clone() for p in params]
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.optim.zero_grad(set_to_none=True)
+                one_step()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        with torch.no_grad():
+            for p, q in zip(params, saved):
+                p.copy_(q)
+        self.reset()
+        self.optim.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            one_step()
+
+    @staticmethod
+    def make_key(loss_fn, x, rhs, lr, gamma, n_iter, dc_type):
+        return (id(loss_fn), tuple(x.shape), x.device, None if rhs is None else tuple(rhs.shape), float(lr),
+                float(gamma), int(n_iter), dc_type)
+
+    def reset(self):
+        with torch.no_grad():
+            for st in self.optim.state.values():
+                st['exp_avg'].zero_(); st['exp_avg_sq'].zero_(); st['step'].zero_()
+
+    def run(self, x, time_step, rhs, num_steps):
+        self.x.copy_(x); self.t.copy_(time_step)
+        if rhs is not None:
+            self.rhs.copy_(rhs)
+        self.reset()
+        for _ in range(num_steps):
+            self.graph.replay()
+
+
 def _adapt(x: Tensor, score, sde: SDE, ray_trafo, loss_fn, time_step: Tensor, rhs: Tensor,
            num_steps: int, lr: float = 1e-3, gamma: float = 1e-3, n_iter: int = 1,
-           dc_type: str = "cg") -> None:
+           dc_type: str = "cg", cuda_graph: Optional[bool] = None) -> None:
     """SCD adaptation: ``num_steps`` Adam steps on the trainable (LoRA / bias)
     parameters of ``score`` through Tweedie -> data consistency -> loss
     (reference :220-260).  Gradients flow through A, A* (CUDA kernels via their
-    autograd Functions) and every CG recurrence."""
+    autograd Functions) and every CG recurrence.
+
+    ``cuda_graph`` (default: environment variable ``SCD_ADAPT_CUDA_GRAPH=1``): capture one Adam step -- score
+    model included -- in a CUDA graph and replay it (:class:`_AdaptGraph`); needs the fused objective (standard
+    adaptation loss on the CUDA operator) and a score model that is safe to capture."""
     op = _make_op(ray_trafo, gamma)
     assert _has_lora_active(score=score)
     score.eval()
+    if cuda_graph is None:
+        cuda_graph = os.environ.get('SCD_ADAPT_CUDA_GRAPH') == '1'
+    if cuda_graph and adapt_objective_applies(x, rhs, loss_fn, sde, dc_type):
+        g = getattr(score, '_scd_adapt_graph', None)
+        key = _AdaptGraph.make_key(loss_fn, x, rhs, lr, gamma, n_iter, dc_type)
+        if g is None or g.key != key:
+            with torch.enable_grad():
+                g = _AdaptGraph(score, sde, loss_fn, x, time_step, rhs, lr, gamma, n_iter, dc_type)
+            object.__setattr__(score, '_scd_adapt_graph', g)
+        g.run(x, time_step, rhs, num_steps)
+        return
     optim = torch.optim.Adam(score.parameters(), lr=lr)
     for _ in range(num_steps):
         optim.zero_grad()

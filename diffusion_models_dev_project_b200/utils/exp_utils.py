@@ -120,7 +120,8 @@ def get_standard_adapted_sampler(args, config, score, sde, ray_trafo, observatio
     loss_fn = AdaptationLoss(observation, ray_trafo, float(args.tv_penalty))     # callable: loss_fn(x=...)
 
     adapt_fn = functools.partial(_adapt, score=score, sde=sde, loss_fn=loss_fn,
-                                 num_steps=int(args.num_optim_step), lr=float(args.lr))
+                                 num_steps=int(args.num_optim_step), lr=float(args.lr),
+                                 cuda_graph=getattr(args, 'adapt_cuda_graph', None))
     predictor = functools.partial(
         adapted_ddim_sde_predictor, score=score, sde=sde, adapt_fn=adapt_fn, add_cg=args.add_cg,
         dc_type=args.dc_type, rhs=ray_trafo.trafo_adjoint(observation),

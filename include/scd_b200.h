@@ -250,7 +250,7 @@ int scd_bp_host(const scd_geom_t *g, const float *sino_host, float *img_host,
 /* Introspection used by the tests, the bench and the launch heuristics.      */
 int scd_geom_info(const scd_geom_t *g, int32_t *n0, int32_t *n1,
                   int32_t *n_angles, int32_t *n_det);
-/* Number of kernels this library has launched on the calling thread since
+/* Number of kernels this library has launched in this process (all threads) since
  * the last reset (the bench reports it as gpu_launches).                     */
 int64_t scd_launch_count(void);
 void    scd_launch_count_reset(void);

@@ -182,8 +182,11 @@ def test_cg_gradient_fused_reverse_sweep_equals_autograd():
         assert rel_l2(gb.cpu().numpy(), gb_ref.cpu().numpy()) < 1e-4, k
 
 
-def test_adapted_sampling_matches_reference_chain(golden, monkeypatch):
-    """BASELINE config 5 (SCD adapted sampling): factory -> `_adapt` (Adam through Tweedie, CG, A, A* and
+@pytest.mark.parametrize('cuda_graph', [False, True])
+def test_adapted_sampling_matches_reference_chain(golden, monkeypatch, cuda_graph):
+    """(cuda_graph: the Adam step -- score model, scd_adapt_fwd / scd_adapt_bwd, optimizer -- captured once and
+    replayed, samplers/utils.py:_AdaptGraph.)
+    BASELINE config 5 (SCD adapted sampling): factory -> `_adapt` (Adam through Tweedie, CG, A, A* and
     the fused adaptation loss) -> adapted predictor -> sampler on the CUDA kernels, against the outputs
     of the reference's own get_standard_adapted_sampler / _adapt / adapted_ddim_sde_predictor /
     BaseSampler (tests/golden/make_golden.py:adapted_fixture; operator = oracle with ODL's gradient
@@ -198,7 +201,9 @@ def test_adapted_sampling_matches_reference_chain(golden, monkeypatch):
     y = torch.from_numpy(d['y']).cuda()
     for dc in ('cg', 'gd'):
         score = AdaptableScore(r=2, seed=0).cuda()
-        sampler = E.get_standard_adapted_sampler(adapted_args(dc), adapted_config(2, 'cuda'), score, pkg.DDPM(), rt,
+        args = adapted_args(dc)
+        args.adapt_cuda_graph = cuda_graph
+        sampler = E.get_standard_adapted_sampler(args, adapted_config(2, 'cuda'), score, pkg.DDPM(), rt,
                                                  observation=y, device='cuda')
         torch.manual_seed(13)
         recon = sampler.sample(logging=False).cpu().numpy()
@@ -207,6 +212,7 @@ def test_adapted_sampling_matches_reference_chain(golden, monkeypatch):
             ref = d['param_%s_%s' % (dc, name)]
             assert np.allclose(prm.detach().cpu().numpy(), ref, atol=2e-5), (dc, name, prm, ref)
         assert score.adapter.scale == 1.0
+        assert (getattr(score, '_scd_adapt_graph', None) is not None) == cuda_graph
 
 
 def test_dds_256_reconstruction_psnr_parity(golden, monkeypatch):
