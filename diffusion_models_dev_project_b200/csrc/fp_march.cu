@@ -22,13 +22,14 @@
 //                 producer warp with cp.async.bulk (TMA unit) into an mbarrier ring
 //                 (full/empty barriers; no CTA-wide barrier inside the march).
 //   il image      groups of >= 4 samples need no packed copy at all: the image is kept
-//                 sample-interleaved, img_il[group][k0][k1][SB] (no pads), and every strip row is
-//                 fetched by a 4-D TENSOR copy (cp.async.bulk.tensor.4d, SASS UTMALDG): class 0 (rows =
-//                 image rows) takes boxes {SB, pixels, 1, 1} into the strip layout [row][pixel][SB]
-//                 of the packed path; class 1 (rows = image columns) takes boxes {SB, TR, pixels, 1}
-//                 -- TR*SB*4-byte pieces gathered with the image's row stride -- which land
-//                 PIXEL-MAJOR, [pixel][row][SB]: the transposed orientation is never materialised in
-//                 HBM.  Zero pad pixels / pad rows come from the unit's out-of-bounds fill.  In the
+//                 sample-interleaved, img_il[group][k0][k1][SB] (no pads).  Class 0 (strip rows = image
+//                 rows): a row is one contiguous byte range -> one 1-D bulk copy per strip row into the
+//                 row-major strip [row][pixel][SB] of the packed path (pad pixels zeroed once in shared
+//                 memory).  Class 1 (strip rows = image columns): 3-D TENSOR copies
+//                 (cp.async.bulk.tensor.3d, SASS UTMALDG) with boxes {TR*SB, pixels, 1} -- TR*SB*4-byte
+//                 pieces gathered with the image's row stride -- which land PIXEL-MAJOR,
+//                 [pixel][row][SB]: the transposed orientation is never materialised in HBM; its zero
+//                 pad pixels / pad rows come from the unit's out-of-bounds fill.  In the
 //                 pixel-major layout the rays of a quarter-warp visit the rows of a strip in
 //                 different (XOR-rotated) orders, so their 128-byte wavefront never collides
 //                 whatever the ray spacing (the row-major layout conflicts when two rays are two
@@ -89,6 +90,7 @@ struct MqParams {
     // maps passed next to this struct; spitch = pixels per shared-memory strip row (nbox boxes of bw pixels)
     int tma;
     int spitch[2], nbox[2], bw[2];
+    const float *zero_row;   // >= max(n0, n1) * 16 zero floats (source of the strip rows beyond the image)
     // output recurrence of the CG solve (acc_mode != 0): q = A r + beta q_old with
     // beta = sum(rr_new_part) / sum(rr_old_part) per sample (q_{k} = A p_k, p_k = r_k + beta p_{k-1});
     // the per-sample beta is also stored to beta_out for the backprojector's direction update
@@ -268,13 +270,13 @@ __device__ __forceinline__ void mq_bulk_g2s(void *dst, const void *src, unsigned
                  :: "r"(mq_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mq_smem_u32(bar)) : "memory");
 }
 
-// 4-D tiled tensor copy global -> shared through the TMA unit (SASS UTMALDG), completion on an mbarrier;
+// 3-D tiled tensor copy global -> shared through the TMA unit (SASS UTMALDG), completion on an mbarrier;
 // elements outside the tensor are filled with zeros
-__device__ __forceinline__ void mq_tensor_g2s(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
+__device__ __forceinline__ void mq_tensor_g2s(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2,
                                               unsigned long long *bar)
 {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
-                 :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mq_smem_u32(bar)) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+                 :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(mq_smem_u32(bar)) : "memory");
 }
 
 // Tap loads with explicit 32-bit shared-window addresses (a generic pointer would be re-mapped
@@ -404,7 +406,7 @@ struct __align__(8) MqAng { float scale; int id; };
 // NWT   warps per CTA: NWT-1 marching warps + one producer warp
 template <int V, int LPR, int NSLOT, int TR, int NWT>
 __global__ void __launch_bounds__(32 * NWT, 1)
-fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1)
+fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm1)
 {
     typedef MqVec<V> LD;
     typedef typename LD::T VT;
@@ -477,7 +479,18 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const
         const float2 t = __ldg(P.angt + pos0 + tid);
         MqAng a; a.scale = t.x; a.id = __float_as_int(t.y); ang[tid] = a;
     }
-    __syncthreads();                              // mbarrier init + tables visible
+    if (P.tma && cls == 0) {
+        // pad pixels (1 left, >= 2 right) of every row of every ring buffer: zero once, the row copies never touch them
+        const int padr = pitch - 1 - ncols;
+        const int per_row = (1 + padr) * SB;
+        for (int i = tid; i < NBUF * TR * per_row; i += NTHR) {
+            const int row = i / per_row, k = i - row * per_row;
+            float *rp = reinterpret_cast<float *>(tile0 + (size_t)row * row_bytes);
+            rp[k < SB ? k : (size_t)(ncols + 1) * SB + (k - SB)] = 0.f;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes vs the async copies
+    }
+    __syncthreads();                              // mbarrier init + tables (+ pads) visible
     scd_stamp(P.dbg, 1);                          // tables done
     scd_pdl_wait();                               // the pack pass has completed: packed image visible
     scd_pdl_trigger();
@@ -505,29 +518,43 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const
 
     if (warp == NW) {
         // ------------------------------ producer warp ------------------------------
-        if (P.tma) {
-            // Class 0 (rows = image rows): one tensor copy per (strip row, box of bw pixels), lane = rr * nbox + box,
-            // landing row-major [row][pixel][SB].  Class 1 (rows = image columns): one copy per box covering all TR
-            // rows, box {SB, TR, bw}: the unit gathers TR*SB*4-byte pieces with the image's row stride and lands
-            // them pixel-major [pixel][row][SB].  Pixel -1, pixels >= ncols and rows >= nrows are out of bounds:
-            // zero fill.
-            const CUtensorMap *tm = cls == 0 ? &tm0 : &tm1;
-            const int nbox = P.nbox[cls], bw = P.bw[cls];
-            const int rr = cls == 0 ? lane / nbox : 0, bx = cls == 0 ? lane - rr * nbox : lane;
-            const bool mine = cls == 0 ? lane < TR * nbox : lane < nbox;
-            const unsigned dst0 = mq_smem_u32(tile0) +
-                (cls == 0 ? (unsigned)rr * row_bytes + (unsigned)(bx * bw * SB * 4) : (unsigned)(bx * bw) * (unsigned)(TR * SB * 4));
-            const int cpix = bx * bw - 1;
+        if (P.tma && cls == 0) {
+            // Class 0 (rows = image rows): a row of the interleaved image is one contiguous byte range -> one 1-D bulk
+            // copy per strip row (lane rr), landing behind the left pad pixel of the row-major strip [row][pixel][SB];
+            // the pad pixels of every ring buffer were zeroed above and are never overwritten.  Rows beyond the image
+            // (the row count is rounded up to x8) are copied from a zero row.
+            const bool mine = lane < TR;
+            const unsigned dst0 = mq_smem_u32(tile0) + (unsigned)lane * row_bytes + (unsigned)(SB * 4);
+            const unsigned nbytes = (unsigned)ncols * (unsigned)(SB * 4);
+            const float *img0 = P.img + (size_t)grp * nrows * ncols * SB;
+            int bi = 0; unsigned ph = 0;
+            for (int st = 0; st < nst; ++st) {
+                if (st >= NBUF) mq_mbar_wait(&empty[bi], ph ^ 1u);      // previous use of this buffer released
+                if (lane == 0) mq_mbar_expect_tx(&full[bi], TR * nbytes);
+                __syncwarp();
+                if (mine) {
+                    const int row = r_begin + st * TR + lane;
+                    const float *srow = row < nrows ? img0 + (size_t)row * ncols * SB : P.zero_row;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                                 :: "r"(dst0 + (unsigned)bi * strip_bytes), "l"(srow), "r"(nbytes), "r"(mq_smem_u32(&full[bi])) : "memory");
+                }
+                if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+            }
+        } else if (P.tma) {
+            // Class 1 (rows = image columns): the image as a 3-D tensor (n1*SB, n0, groups); one copy per box of bw
+            // pixels covering all TR rows, box {TR*SB, bw, 1}: the unit gathers TR*SB*4-byte pieces with the image's
+            // row stride and lands them pixel-major [pixel][row][SB].  Pixel -1, pixels >= ncols and rows >= nrows
+            // are out of bounds: zero fill.
+            const int nbox = P.nbox[1], bw = P.bw[1];
+            const bool mine = lane < nbox;
+            const unsigned dst0 = mq_smem_u32(tile0) + (unsigned)(lane * bw) * (unsigned)(TR * SB * 4);
+            const int cpix = lane * bw - 1;
             int bi = 0; unsigned ph = 0;
             for (int st = 0; st < nst; ++st) {
                 if (st >= NBUF) mq_mbar_wait(&empty[bi], ph ^ 1u);      // previous use of this buffer released
                 if (lane == 0) mq_mbar_expect_tx(&full[bi], strip_bytes);
                 __syncwarp();
-                if (mine) {
-                    const int row = r_begin + st * TR + rr;
-                    if (cls == 0) mq_tensor_g2s(dst0 + (unsigned)bi * strip_bytes, tm, 0, cpix, row, grp, &full[bi]);
-                    else          mq_tensor_g2s(dst0 + (unsigned)bi * strip_bytes, tm, 0, row, cpix, grp, &full[bi]);
-                }
+                if (mine) mq_tensor_g2s(dst0 + (unsigned)bi * strip_bytes, &tm1, (r_begin + st * TR) * SB, cpix, grp, &full[bi]);
                 if (++bi == NBUF) { bi = 0; ph ^= 1u; }
             }
         } else if (lane == 0) {
@@ -654,7 +681,10 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const
     }
     scd_stamp(P.dbg, 6);                          // output written
     if (CS > 1) cluster.sync();                   // keep red alive until every rank has read it
-    scd_stamp(P.dbg, 7);
+#ifdef SCD_DEBUG_STAMPS
+    if (P.dbg && threadIdx.x == 0)                // slot 7: class and angle count of the unit (tools/timeline.py --by-class)
+        P.dbg[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)(cls * 1000 + na);
+#endif
 }
 
 // ------------------------------------------------------------- host side ---
@@ -831,13 +861,13 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max, bool tma 
 // first: list scheduling) and keeps the split with the smallest simulated makespan.
 struct MqPlan { int n_runs; MqRun runs[MQ_MAX_RUNS]; int units, n_big; };
 
-static double mq_makespan(const int *sizes, const int *counts, int nkinds, int jobs_per_unit, int machines)
+static double mq_makespan(const int *sizes, const int *counts, int nkinds, int jobs_per_unit, int machines, double fixed)
 {
     // machines take jobs in launch order; all jobs of one kind cost the same
     std::vector<double> load((size_t)machines, 0.0);
     std::make_heap(load.begin(), load.end(), std::greater<double>());
     for (int k = 0; k < nkinds; ++k) {
-        const double cost = sizes[k] + 0.25;
+        const double cost = sizes[k] + fixed;         // angles + fixed share (strip fetches, tables, output) in units of one angle
         for (long j = 0; j < (long)counts[k] * jobs_per_unit; ++j) {
             std::pop_heap(load.begin(), load.end(), std::greater<double>());
             load.back() += cost;
@@ -865,6 +895,7 @@ static MqPlan mq_plan(const scd_geom *g, const MqConfig &c, int angle_lo, int an
     // (plus one remainder chunk); the same (t1, t2) for both classes, clipped to the class size
     int best_t1 = 0, best_t2 = 0;
     double best = -1.0;
+    const double fixed = g->tune_fp_plan_cost > 0 ? g->tune_fp_plan_cost / 100.0 : 0.25;
     const int nmax = std::max(cnt[0], cnt[1]);
     const bool search = NA > 2 && g->tune_fp_plan != 1 && (long)c.groups * nmax * 2 <= 4096;
     for (int t1 = 0; t1 <= (search ? std::min(nmax, 2 * NA) : 0); ++t1)
@@ -882,7 +913,7 @@ static MqPlan mq_plan(const scd_geom *g, const MqConfig &c, int angle_lo, int an
             for (int cl = 0; cl < 2; ++cl) if (rem[cl]) { sizes[nk] = rem[cl]; counts[nk++] = 1; }
             sizes[nk] = 2; counts[nk++] = pairs[0] + pairs[1];
             sizes[nk] = 1; counts[nk++] = single[0] + single[1];
-            const double m = mq_makespan(sizes, counts, nk, c.groups, machines);
+            const double m = mq_makespan(sizes, counts, nk, c.groups, machines, fixed);
             if (best < 0 || m < best - 1e-9) { best = m; best_t1 = t1; best_t2 = t2; }
         }
     MqPlan pl;
@@ -924,7 +955,7 @@ static int mq_launch_t(const MqParams &P, const CUtensorMap *tms, dim3 grid, siz
 {
     static ScdSmemAttr attr = {};        // per instantiation
     SCD_CUDA(scd_ensure_smem(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, attr, device, smem));
-    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P, tms[0], tms[1]));
+    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P, tms[0]));
     SCD_LAUNCH_CHECK("fp_march_kernel");
     return 0;
 }
@@ -947,23 +978,20 @@ static MqEncodeFn mq_encoder()
     return fn;
 }
 
-// img_il[group][k0][k1][SB] as a 4-D tensor (SB, n1, n0, groups); class 0 boxes run along k1, class 1 along k0
+// Class-1 strips: img_il[group][k0][k1][SB] as a 3-D tensor (n1*SB, n0, groups) -- an image row is one contiguous
+// run of n1*SB floats -- with boxes of TR image columns x bw pixels: {TR*SB, bw, 1}
 static int mq_make_maps(const scd_geom *g, const float *img_il, const MqConfig &c, CUtensorMap tms[2])
 {
     MqEncodeFn enc = mq_encoder();
     if (!enc) { scd_set_error("scd_fp: cuTensorMapEncodeTiled is not available in this driver"); return SCD_E_NODEVICE; }
-    const cuuint64_t dims[4] = {(cuuint64_t)c.SB, (cuuint64_t)g->n1, (cuuint64_t)g->n0, (cuuint64_t)c.groups};
-    const cuuint64_t strides[3] = {(cuuint64_t)c.SB * 4, (cuuint64_t)g->n1 * c.SB * 4, (cuuint64_t)g->n0 * g->n1 * c.SB * 4};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int cls = 0; cls < 2; ++cls) {
-        // class 0: one strip row of bw pixels; class 1: TR image columns x bw pixels (lands pixel-major)
-        const cuuint32_t box[4] = {(cuuint32_t)c.SB, cls == 0 ? (cuuint32_t)c.bw[0] : (cuuint32_t)c.TR,
-                                   cls == 0 ? 1u : (cuuint32_t)c.bw[1], 1u};
-        const CUresult r = enc(&tms[cls], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)img_il, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { scd_set_error("scd_fp: cuTensorMapEncodeTiled failed (%d)", (int)r); return SCD_E_INVALID; }
-    }
+    const cuuint64_t dims[3] = {(cuuint64_t)g->n1 * c.SB, (cuuint64_t)g->n0, (cuuint64_t)c.groups};
+    const cuuint64_t strides[2] = {(cuuint64_t)g->n1 * c.SB * 4, (cuuint64_t)g->n0 * g->n1 * c.SB * 4};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)(c.TR * c.SB), (cuuint32_t)c.bw[1], 1u};
+    const CUresult r = enc(&tms[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)img_il, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { scd_set_error("scd_fp: cuTensorMapEncodeTiled failed (%d)", (int)r); return SCD_E_INVALID; }
     return 0;
 }
 
@@ -973,12 +1001,12 @@ static int mq_march(const scd_geom *g, const MqConfig &c, MqParams &P, const CUt
 {
     // the plan depends only on the geometry, the configuration and the angle range: keep the last one
     // (the search simulates a few hundred schedules, too slow to repeat at every launch)
-    struct PlanKey { unsigned long long g; int lo, hi, groups, NA, CS, plan, sm; };
-    static thread_local PlanKey last_key = {0ull, 0, 0, 0, 0, 0, 0, 0};
+    struct PlanKey { unsigned long long g; int lo, hi, groups, NA, CS, plan, sm, cost; };
+    static thread_local PlanKey last_key = {0ull, 0, 0, 0, 0, 0, 0, 0, 0};
     static thread_local MqPlan last_plan;
-    const PlanKey key = {g->id, angle_lo, angle_hi, c.groups, c.NA, c.CS, g->tune_fp_plan, g->sm_count};
+    const PlanKey key = {g->id, angle_lo, angle_hi, c.groups, c.NA, c.CS, g->tune_fp_plan, g->sm_count, g->tune_fp_plan_cost};
     const bool same = key.g == last_key.g && key.lo == last_key.lo && key.hi == last_key.hi && key.groups == last_key.groups &&
-                      key.NA == last_key.NA && key.CS == last_key.CS && key.plan == last_key.plan && key.sm == last_key.sm;
+                      key.NA == last_key.NA && key.CS == last_key.CS && key.plan == last_key.plan && key.sm == last_key.sm && key.cost == last_key.cost;
     if (!same) {
         last_plan = mq_plan(g, c, angle_lo, angle_hi);
         last_key = key;
@@ -1090,6 +1118,7 @@ int scd_launch_fp_ilimg(const scd_geom *g, const float *img_il, float *sino, flo
     if (c.smem > (size_t)g->smem_optin || !c.NSLOT) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
     MqParams P;
     mq_fill_params(g, c, P, sino, sino_il, batch, ncls);
+    P.img = img_il; P.zero_row = g->d_zero_row;
     if (acc) {
         P.acc_mode = 1;
         P.rr_new_part = acc->rr_new_part; P.rr_new_n = acc->rr_new_n;
@@ -1113,8 +1142,7 @@ bool scd_il_image_ok(const scd_geom *g, int batch)
     if (SB < 4 || !mq_encoder()) return false;
     int sp[2], nb[2], bw[2];
     mq_tma_rows(g, SB, sp, nb, bw);
-    const int trmax = SB >= 16 ? 4 : 8;
-    return nb[0] * trmax <= 32 && nb[1] <= 32;
+    return nb[1] <= 32;                                 // one lane of the producer warp per class-1 box
 }
 
 size_t scd_il_image_bytes(const scd_geom *g, int batch)

@@ -161,6 +161,8 @@ extern "C" int scd_geom_create(const scd_geom_desc *d, scd_geom_t **out)
         (ce = cudaMemcpy(g->d_rayt, rayt.data(), sizeof(float2) * rayt.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_angt, sizeof(float2) * na)) != cudaSuccess ||
         (ce = cudaMemcpy(g->d_angt, angt.data(), sizeof(float2) * na, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (ce = cudaMalloc(&g->d_zero_row, (size_t)std::max(d->n0, d->n1) * 16 * sizeof(float))) != cudaSuccess ||
+        (ce = cudaMemset(g->d_zero_row, 0, (size_t)std::max(d->n0, d->n1) * 16 * sizeof(float))) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_fp, sizeof(FpAngle) * na)) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_bp, sizeof(BpAngle) * na)) != cudaSuccess ||
         (ce = cudaMalloc(&g->d_order, sizeof(int) * na)) != cudaSuccess ||
@@ -182,6 +184,7 @@ extern "C" int scd_geom_destroy(scd_geom_t *g)
     if (g->d_order) cudaFree(g->d_order);
     if (g->d_rayt) cudaFree(g->d_rayt);
     if (g->d_angt) cudaFree(g->d_angt);
+    if (g->d_zero_row) cudaFree(g->d_zero_row);
     free(g->h_fp); free(g->h_bp); free(g->h_order);
     free(g);
     return 0;
@@ -209,6 +212,7 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_cluster")) g->tune_fp_cluster = value;
     else if (!strcmp(key, "fp_plan")) g->tune_fp_plan = value;
     else if (!strcmp(key, "fp_source")) g->tune_fp_source = value;
+    else if (!strcmp(key, "fp_plan_cost")) g->tune_fp_plan_cost = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
     else if (!strcmp(key, "bp_share")) g->tune_bp_share = value;
     else if (!strcmp(key, "bp_rows")) {

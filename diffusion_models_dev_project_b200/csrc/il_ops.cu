@@ -327,7 +327,7 @@ int scd_il_vec_blocks(const scd_geom *g, int batch)
     long nb = (4L * g->sm_count + groups - 1) / groups;
     const long cap = (long)((f4 + IL_THREADS - 1) / IL_THREADS);
     if (nb > cap) nb = cap;
-    if (nb > 64) nb = 64;
+    if (nb > g->sm_count) nb = g->sm_count;      // one block per SM for a single group; the consumers add the partials
     if (nb < 1) nb = 1;
     return (int)nb;
 }

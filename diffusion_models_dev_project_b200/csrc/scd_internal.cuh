@@ -127,13 +127,14 @@ struct scd_geom {
     float2  *d_rayt;      // [n_angles][n_det] (u0 + 1, b): start position (row 0) and slope of every ray, from fp64;
                           // rows in order[] order (position p holds angle order[p])
     float2  *d_angt;      // [n_angles] (scale, id as int bits) in order[] order
+    float   *d_zero_row;  // max(n0, n1) * 16 zero floats: source of projector strip rows beyond the image
     // host copies
     FpAngle *h_fp;
     BpAngle *h_bp;
     int     *h_order;
     int n_cls0;           // number of class-0 angles (they come first in order[])
     // tuning overrides (0 = heuristic)
-    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan;
+    int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan, tune_fp_plan_cost;
     int tune_bp_tile, tune_bp_share, tune_bp_rows;
     int tune_fp_source;   // 1: force the packed-copy path of the projector (A/B runs, tests)
     // sample-interleaved sinogram rows (bp_tile.cu): il_padl zero bins, n_det bins, zero bins up to il_nb

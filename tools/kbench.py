@@ -30,7 +30,7 @@ def timed(fn, iters, flush):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--kernel', default='fp', choices=['fp', 'bp', 'cg'])
+    ap.add_argument('--kernel', default='fp', choices=['fp', 'march', 'bp', 'cg'])
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--im', type=int, default=256)
     ap.add_argument('--angles', type=int, default=60)
@@ -48,10 +48,13 @@ def main():
     nbytes = 4 * (a.im * a.im + rt.obs_shape[0] * rt.obs_shape[1]) * a.batch
 
     def run(tune):
-        keys = ['fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'bp_tile', 'bp_share', 'bp_rows']
+        keys = ['fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'fp_plan_cost', 'fp_source', 'bp_tile', 'bp_share', 'bp_rows']
         rt.set_tuning(dev, **{k: tune.get(k, 0) for k in keys})
         if a.kernel == 'fp':
             fn = lambda: rt._fp(x)          # noqa: E731
+        elif a.kernel == 'march':           # the projector alone on an interleaved image (as inside CG)
+            x_il = rt._img_il(x)
+            fn = lambda: rt._fp_ilimg(x_il, a.batch)   # noqa: E731
         elif a.kernel == 'bp':
             fn = lambda: rt._bp(y, 0.01, addend=p, addend_scale=1.0)   # noqa: E731
         else:

@@ -64,16 +64,25 @@ def main():
         np.save(a.dump, s[:4096])
     s = s[s[:, 0] > 0]
     t0 = s[:, 0].min()
-    print('%s at batch %d: %d CTAs, span %.1f us' % (a.kernel, a.batch, len(s), (s.max() - t0) / 1e3))
-    for k, name in enumerate(NAMES[a.kernel]):
+    print('%s at batch %d: %d CTAs, span %.1f us' % (a.kernel, a.batch, len(s), (s[:, :7].max() - t0) / 1e3))
+    for k, name in enumerate(NAMES[a.kernel][:7] if a.kernel == 'fp' else NAMES[a.kernel]):
         col = s[:, k]
         col = col[col > 0]
         if len(col) == 0:
             continue
         rel = (col - t0) / 1e3
         print('  %-22s min %7.2f  med %7.2f  max %7.2f us' % (name, rel.min(), np.median(rel), rel.max()))
-    dur = (s[:, [c for c in range(8) if (s[:, c] > 0).all()][-1]] - s[:, 0]) / 1e3
+    dur = (s[:, [c for c in range(7 if a.kernel == 'fp' else 8) if (s[:, c] > 0).all()][-1]] - s[:, 0]) / 1e3
     print('  per-CTA duration       min %7.2f  med %7.2f  max %7.2f us' % (dur.min(), np.median(dur), dur.max()))
+    if a.kernel == 'fp':
+        tag = s[:, 7]
+        march = (s[:, 4] - s[:, 3]) / 1e3
+        total = (s[:, 6] - s[:, 0]) / 1e3
+        print('  by (class, angles per unit): CTAs, median duration, median march phase')
+        for t in sorted(set(tag.tolist())):
+            m = tag == t
+            print('    class %d, %d angle(s): %4d CTAs  %7.1f us  march %7.1f us' % (t // 1000, t % 1000, m.sum(),
+                                                                                np.median(total[m]), np.median(march[m])))
     if a.mod:
         idx = np.arange(len(dur))
         march = (s[:, 4] - s[:, 3]) / 1e3
