@@ -118,7 +118,22 @@ def stack_block(dev, world, rank, im=501, angles=1200, slices=501, chunk=128, it
                                 iters, dev, world) * (slices / nloc)
     if shp is not None:
         out['op_ms_peer'] = _timed(lambda: shp.normal_apply(x, gamma), iters, dev, world)
-    out['op_ms'] = min(v for v in (out['op_ms_nccl'], out.get('op_ms_peer')) if v is not None)
+        # the owner's reduction storing once to the NVSwitch multicast address instead of once per peer
+        try:
+            shm = AngleShardedRayTrafo(rt, chunk=chunk, reduce='peer', multicast=True)
+            shm.normal_apply(xs, gamma)
+            has_mc = 1.0 if shm._peer is not None and shm._peer.use_multicast else 0.0
+        except Exception as e:
+            out['multicast_unavailable'] = '%s: %s' % (type(e).__name__, str(e)[:200])
+            has_mc = 0.0
+        ok = torch.tensor([has_mc], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) > 0:
+            n_full = rt.normal_apply(xs, gamma)
+            out['parity']['op_peer_multicast_rel_l2'] = float((shm.normal_apply(xs, gamma) - n_full).norm() / n_full.norm())
+            out['op_ms_peer_multicast'] = _timed(lambda: shm.normal_apply(x, gamma), iters, dev, world)
+        del shm
+    out['op_ms'] = min(v for v in (out['op_ms_nccl'], out.get('op_ms_peer'), out.get('op_ms_peer_multicast')) if v is not None)
     out['exposed_collective_ms'] = max(0.0, out['op_ms_nccl'] - out['op_local_ms'])
     out['overlap_hidden_ms'] = max(0.0, out['allreduce_alone_ms'] - out['exposed_collective_ms'])
     bytes_rank = 4 * (im * im + (hi - lo) * n_det) * slices       # per-rank algorithmic bytes of A (and of A*)

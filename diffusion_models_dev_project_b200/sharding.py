@@ -52,10 +52,13 @@ class AngleShardedRayTrafo:
     Inference-only: the sharded operators do not record autograd graphs and raise if an input requires grad.
     """
 
-    def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl'):
+    def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl', multicast=None):
         if reduce not in ('nccl', 'peer'):
             raise ValueError("reduce must be 'nccl' or 'peer'")
         self.reduce = reduce
+        # reduce='peer': store the reduced bands once to the NVSwitch multicast address instead of once per peer
+        # (None: environment variable SCD_PEER_MULTICAST=1)
+        self.multicast = (os.environ.get('SCD_PEER_MULTICAST') == '1') if multicast is None else bool(multicast)
         self._peer = None
         self.base = base
         self.group = group
@@ -126,8 +129,9 @@ class AngleShardedRayTrafo:
             else:
                 pending.append(dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         if on_cuda:
+            # the caller's stream waits for the reductions: whatever touches `out` (or its memory, once freed)
+            # afterwards is ordered behind the side stream's work, so no record_stream bookkeeping is needed
             torch.cuda.current_stream(out.device).wait_stream(self._comm_stream)
-            out.record_stream(self._comm_stream)
         else:
             for work in pending:
                 work.wait()
@@ -230,7 +234,7 @@ class _PeerReduce:
         self.result_mc = [int(getattr(h, 'multicast_ptr', 0) or 0) for h in hr]
         # opt-in (SCD_PEER_MULTICAST=1): measured slower than per-peer stores on 2 GPUs (scalar strong.sys stores),
         # not yet measured on 8, where it divides the owner's outgoing traffic by the number of GPUs
-        self.use_multicast = all(self.result_mc) and os.environ.get('SCD_PEER_MULTICAST') == '1'
+        self.use_multicast = all(self.result_mc) and sh.multicast
         self.calls = 0
         self.flag = torch.zeros(1, device=device)
         self.comm = torch.cuda.Stream(device=device)
