@@ -796,6 +796,11 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max, bool tma 
         // (B = 32: 72 -> 67 us); many CTAs: the 15-warp shape with more registers wins (B = 256)
         const int units4 = c.groups * ((n_cls_max + 3) / 4) * 2;
         if (units4 * 4 <= 2 * g->sm_count) c.NWT = 24;
+        // many CTAs per SM in sequence (several waves): more warps per CTA hide the tap latency better as long as
+        // four angles per CTA still fit the smaller register budget (measured on the tensor-copy path, 256^2:
+        // B = 128: 198.7 -> 192.0 us with 24 warps, B = 256: 359.9 -> 340.9 us with 32; neutral or worse below)
+        else if (c.LPR == 4 && units4 * 2 >= 3 * g->sm_count && 4 * nchunk <= 6 * 31) c.NWT = 32;
+        else if (c.LPR == 4 && units4 * 4 >= 3 * g->sm_count && 4 * nchunk <= 8 * 23) c.NWT = 24;
     }
     if (g->tune_fp_threads == 1024 && c.V == 4 && c.LPR >= 2) c.NWT = 32;
     else if (g->tune_fp_threads == 768 && c.V == 4) c.NWT = 24;
