@@ -801,6 +801,9 @@ static MqConfig mq_choose(const scd_geom *g, int batch, int n_cls_max, bool tma 
         // B = 128: 198.7 -> 192.0 us with 24 warps, B = 256: 359.9 -> 340.9 us with 32; neutral or worse below)
         else if (c.LPR == 4 && units4 * 2 >= 3 * g->sm_count && 4 * nchunk <= 6 * 31) c.NWT = 32;
         else if (c.LPR == 4 && units4 * 4 >= 3 * g->sm_count && 4 * nchunk <= 8 * 23) c.NWT = 24;
+        // wide detectors (501^2: 711 bins = 89 chunks): four angles per CTA fit no shape, two fit 24 warps as well
+        // as 16 (501^2 x 128 slices x 150 angles: 2058 -> 1891 us)
+        else if (c.LPR == 4 && units4 * 4 >= 3 * g->sm_count && 4 * nchunk > 13 * 15 && 2 * nchunk <= 8 * 23) c.NWT = 24;
     }
     if (g->tune_fp_threads == 1024 && c.V == 4 && c.LPR >= 2) c.NWT = 32;
     else if (g->tune_fp_threads == 768 && c.V == 4) c.NWT = 24;
