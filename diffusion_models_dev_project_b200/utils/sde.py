@@ -111,7 +111,12 @@ class DDPM(SDE):
         self._tables = {}
 
     def alpha_bar_table(self, device=None) -> torch.Tensor:
-        """fp32 tensor ``[num_steps + 1]``: entry ``k`` is alpha-bar at time ``k - 1``."""
+        """fp32 tensor ``[num_steps + 1]``: entry ``k`` is alpha-bar at time ``k - 1``.
+
+        The fp64 cumulative product is formed on the host and the rounded fp32 table moved to ``device`` once.
+        The reference forms it on ``t.device`` at every call (src/utils/sde.py:172-174): bit-identical to this
+        table when the reference runs on CPU (the golden vectors); a reference running on a GPU may differ in the
+        last bit (the fp64 ``cumprod`` of the two devices need not associate the same way)."""
         key = str(device)
         tab = self._tables.get(key)
         if tab is None:

@@ -133,6 +133,35 @@ def test_no_write_outside_the_buffers(im_shape, num_angles, batches):
         _lib.check(lib.scd_tv_grad(img.ptr, tvg.ptr, B, im_shape[0], im_shape[1], st), 'scd_tv_grad')
         assert torch.isfinite(tvp.floats(tvp.nbytes // 4)).all() and torch.isfinite(tvg.floats(B, n_img)).all()
         assert abs(float(tvp.floats(tvp.nbytes // 4).sum()) - float(pkg.tv_loss(x))) <= 1e-4 * float(pkg.tv_loss(x))
+        # ---- ramp filter of fbp
+        filt = G('ramp_out', B * n_sino * 4)
+        _lib.check(lib.scd_ramp_filter(h.ptr, sino.ptr, filt.ptr, B, st), 'scd_ramp_filter')
+        assert torch.equal(filt.floats(B, 1, na, nd), rt.ramp_filter(ref_y))
+        # ---- sample-interleaved images (batches >= 3)
+        n_il = lib.scd_img_il_bytes(h.ptr, B)
+        assert (n_il > 0) == (B >= 3)
+        if n_il:
+            x_il, z_il = G('img_il', n_il), G('bp_il_img', n_il)
+            _lib.check(lib.scd_img_il_pack(h.ptr, img.ptr, x_il.ptr, B, st), 'scd_img_il_pack')
+            back = G('img_unpacked', B * n_img * 4)
+            _lib.check(lib.scd_img_il_unpack(h.ptr, x_il.ptr, back.ptr, B, st), 'scd_img_il_unpack')
+            assert torch.equal(back.floats(B, 1, *im_shape), x)
+            il2 = G('sino_il2', lib.scd_sino_il_buffer_bytes(h.ptr, B))
+            _lib.check(lib.scd_fp_ilimg(h.ptr, x_il.ptr, il2.ptr, B, 0, na, st), 'scd_fp_ilimg')
+            _lib.check(lib.scd_bp_ilimg(h.ptr, il2.ptr, z_il.ptr, B, 0, na, rt.adj_scale, x_il.ptr, 0.0, st), 'scd_bp_ilimg')
+            _lib.check(lib.scd_img_il_unpack(h.ptr, z_il.ptr, back.ptr, B, st), 'scd_img_il_unpack')
+            assert torch.equal(back.floats(B, 1, *im_shape), ref_z)
+        else:
+            assert lib.scd_img_il_pack(h.ptr, img.ptr, img.ptr, B, st) == _lib.SCD_E_INVALID
+        # ---- SCD adaptation objective: forward, reverse sweep (all three data-consistency types)
+        loss, gs = G('adapt_loss', 256), G('adapt_grad', B * n_img * 4)
+        for dc, k in ((0, 2), (1, 1), (2, 1)):
+            aw = G('adapt_work_%d' % dc, lib.scd_adapt_workspace_bytes(h.ptr, B, k))
+            _lib.check(lib.scd_adapt_fwd(h.ptr, img.ptr, s.ptr, rhs.ptr, sino.ptr, t.ptr, abar.data_ptr(), abar.numel(), 0.05, k, dc,
+                                         1e-3, loss.ptr, None, B, aw.ptr, aw.nbytes, st), 'scd_adapt_fwd')
+            _lib.check(lib.scd_adapt_bwd(h.ptr, None, t.ptr, abar.data_ptr(), abar.numel(), 0.05, k, dc, 1e-3,
+                                         rt.adj_scale / rt.geometry.range_weight, gs.ptr, B, aw.ptr, aw.nbytes, st), 'scd_adapt_bwd')
+            assert torch.isfinite(gs.floats(B, n_img)).all() and bool(torch.isfinite(loss.floats(1)).all())
         torch.cuda.synchronize()
         broken = [k for k, g in bufs.items() if not g.intact()]
         assert not broken, 'guard bytes overwritten around %s (shape %r, batch %d)' % (broken, im_shape, B)
