@@ -91,6 +91,7 @@ struct MqParams {
     int tma;
     int spitch[2], nbox[2], bw[2];
     const float *zero_row;   // >= max(n0, n1) * 16 zero floats (source of the strip rows beyond the image)
+    int cls0_pm;             // class 0 fetched pixel-major by tensor copies too (4-D map tm0) instead of row-major bulk rows
     // output recurrence of the CG solve (acc_mode != 0): q = A r + beta q_old with
     // beta = sum(rr_new_part) / sum(rr_old_part) per sample (q_{k} = A p_k, p_k = r_k + beta p_{k-1});
     // the per-sample beta is also stored to beta_out for the backprojector's direction update
@@ -279,6 +280,13 @@ __device__ __forceinline__ void mq_tensor_g2s(unsigned dst, const CUtensorMap *t
                  :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(mq_smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void mq_tensor4_g2s(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3,
+                                               unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n"
+                 :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(mq_smem_u32(bar)) : "memory");
+}
+
 // Tap loads with explicit 32-bit shared-window addresses (a generic pointer would be re-mapped
 // through the cluster window on every access).  volatile: they stay behind the mbarrier wait.
 template <int V> struct MqVec;
@@ -406,7 +414,7 @@ struct __align__(8) MqAng { float scale; int id; };
 // NWT   warps per CTA: NWT-1 marching warps + one producer warp
 template <int V, int LPR, int NSLOT, int TR, int NWT>
 __global__ void __launch_bounds__(32 * NWT, 1)
-fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm1)
+fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1)
 {
     typedef MqVec<V> LD;
     typedef typename LD::T VT;
@@ -479,7 +487,7 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm1)
         const float2 t = __ldg(P.angt + pos0 + tid);
         MqAng a; a.scale = t.x; a.id = __float_as_int(t.y); ang[tid] = a;
     }
-    if (P.tma && cls == 0) {
+    if (P.tma && cls == 0 && !P.cls0_pm) {
         // pad pixels (1 left, >= 2 right) of every row of every ring buffer: zero once, the row copies never touch them
         const int padr = pitch - 1 - ncols;
         const int per_row = (1 + padr) * SB;
@@ -518,7 +526,7 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm1)
 
     if (warp == NW) {
         // ------------------------------ producer warp ------------------------------
-        if (P.tma && cls == 0) {
+        if (P.tma && cls == 0 && !P.cls0_pm) {
             // Class 0 (rows = image rows): a row of the interleaved image is one contiguous byte range -> one 1-D bulk
             // copy per strip row (lane rr), landing behind the left pad pixel of the row-major strip [row][pixel][SB];
             // the pad pixels of every ring buffer were zeroed above and are never overwritten.  Rows beyond the image
@@ -538,6 +546,22 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm1)
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                                  :: "r"(dst0 + (unsigned)bi * strip_bytes), "l"(srow), "r"(nbytes), "r"(mq_smem_u32(&full[bi])) : "memory");
                 }
+                if (++bi == NBUF) { bi = 0; ph ^= 1u; }
+            }
+        } else if (P.tma && cls == 0) {
+            // Class 0, pixel-major: the image as the 4-D tensor (SB, n0, n1, groups) -- rows before pixels, i.e. with
+            // the strides of dimensions 1 and 2 swapped -- and boxes {SB, TR, bw, 1}: SB*4-byte pieces that land
+            // [pixel][row][SB] like class 1, so that the row rotation removes the bank conflicts here too
+            const int nbox = P.nbox[0], bw = P.bw[0];
+            const bool mine = lane < nbox;
+            const unsigned dst0 = mq_smem_u32(tile0) + (unsigned)(lane * bw) * (unsigned)(TR * SB * 4);
+            const int cpix = lane * bw - 1;
+            int bi = 0; unsigned ph = 0;
+            for (int st = 0; st < nst; ++st) {
+                if (st >= NBUF) mq_mbar_wait(&empty[bi], ph ^ 1u);
+                if (lane == 0) mq_mbar_expect_tx(&full[bi], strip_bytes);
+                __syncwarp();
+                if (mine) mq_tensor4_g2s(dst0 + (unsigned)bi * strip_bytes, &tm0, 0, r_begin + st * TR, cpix, grp, &full[bi]);
                 if (++bi == NBUF) { bi = 0; ph ^= 1u; }
             }
         } else if (P.tma) {
@@ -590,7 +614,7 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm1)
                 }
             }
         }
-        if (P.tma && cls == 1)
+        if (P.tma && (cls == 1 || P.cls0_pm))
             mq_march_rows<V, LPR, NSLOT, TR, NW, true>(acc, eidx, livemask, NCH, warp, lane, nst, NBUF, r_begin, ncols,
                                                        row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg);
         else
@@ -963,7 +987,7 @@ static int mq_launch_t(const MqParams &P, const CUtensorMap *tms, dim3 grid, siz
 {
     static ScdSmemAttr attr = {};        // per instantiation
     SCD_CUDA(scd_ensure_smem(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, attr, device, smem));
-    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P, tms[0]));
+    SCD_CUDA(scd_launch_kernel(fp_march_kernel<V, LPR, NSLOT, TR, NWT>, grid, dim3(32 * NWT), smem, st, P.CS, P, tms[0], tms[1]));
     SCD_LAUNCH_CHECK("fp_march_kernel");
     return 0;
 }
@@ -986,20 +1010,33 @@ static MqEncodeFn mq_encoder()
     return fn;
 }
 
-// Class-1 strips: img_il[group][k0][k1][SB] as a 3-D tensor (n1*SB, n0, groups) -- an image row is one contiguous
-// run of n1*SB floats -- with boxes of TR image columns x bw pixels: {TR*SB, bw, 1}
-static int mq_make_maps(const scd_geom *g, const float *img_il, const MqConfig &c, CUtensorMap tms[2])
+// tms[1], class-1 strips: img_il[group][k0][k1][SB] as a 3-D tensor (n1*SB, n0, groups) -- an image row is one
+// contiguous run of n1*SB floats -- with boxes of TR image columns x bw pixels: {TR*SB, bw, 1}.
+// tms[0], class-0 strips fetched pixel-major (optional): the 4-D tensor (SB, n0, n1, groups), boxes {SB, TR, bw, 1}.
+static int mq_make_maps(const scd_geom *g, const float *img_il, const MqConfig &c, CUtensorMap tms[2], bool cls0_pm)
 {
     MqEncodeFn enc = mq_encoder();
     if (!enc) { scd_set_error("scd_fp: cuTensorMapEncodeTiled is not available in this driver"); return SCD_E_NODEVICE; }
-    const cuuint64_t dims[3] = {(cuuint64_t)g->n1 * c.SB, (cuuint64_t)g->n0, (cuuint64_t)c.groups};
-    const cuuint64_t strides[2] = {(cuuint64_t)g->n1 * c.SB * 4, (cuuint64_t)g->n0 * g->n1 * c.SB * 4};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const cuuint32_t box[3] = {(cuuint32_t)(c.TR * c.SB), (cuuint32_t)c.bw[1], 1u};
-    const CUresult r = enc(&tms[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)img_il, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { scd_set_error("scd_fp: cuTensorMapEncodeTiled failed (%d)", (int)r); return SCD_E_INVALID; }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)g->n1 * c.SB, (cuuint64_t)g->n0, (cuuint64_t)c.groups};
+        const cuuint64_t strides[2] = {(cuuint64_t)g->n1 * c.SB * 4, (cuuint64_t)g->n0 * g->n1 * c.SB * 4};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)(c.TR * c.SB), (cuuint32_t)c.bw[1], 1u};
+        const CUresult r = enc(&tms[1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)img_il, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { scd_set_error("scd_fp: cuTensorMapEncodeTiled failed (%d)", (int)r); return SCD_E_INVALID; }
+    }
+    if (cls0_pm) {
+        const cuuint64_t dims[4] = {(cuuint64_t)c.SB, (cuuint64_t)g->n0, (cuuint64_t)g->n1, (cuuint64_t)c.groups};
+        const cuuint64_t strides[3] = {(cuuint64_t)g->n1 * c.SB * 4, (cuuint64_t)c.SB * 4, (cuuint64_t)g->n0 * g->n1 * c.SB * 4};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)c.SB, (cuuint32_t)c.TR, (cuuint32_t)c.bw[0], 1u};
+        const CUresult r = enc(&tms[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)img_il, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { scd_set_error("scd_fp: cuTensorMapEncodeTiled (class 0) failed (%d)", (int)r); return SCD_E_INVALID; }
+    }
     return 0;
 }
 
@@ -1133,8 +1170,14 @@ int scd_launch_fp_ilimg(const scd_geom *g, const float *img_il, float *sino, flo
         P.rr_old_part = acc->rr_old_part; P.rr_old_n = acc->rr_old_n; P.part_stride = acc->part_stride;
         P.beta_out = acc->beta_out;
     }
+    // class 0 pixel-major as well: pays where the row-major layout conflicts most -- 8 samples per pixel (a
+    // quarter-warp holds four rays: 30 % of its wavefronts were conflicts).  Measured at 256^2: B = 8 26.8 -> 24.8 us;
+    // neutral at B = 16 .. 32, -1 % at B = 256, +4 % on the 501^2 shard (16 samples per pixel: 4.5 % conflicts
+    // only, and SB*4-byte pieces instead of whole rows), +4 % at B = 4.  fp_cls0: 1 = always, 2 = never.
+    P.cls0_pm = (g->tune_fp_cls0 == 1 || (g->tune_fp_cls0 == 0 && c.LPR == 2)) && c.nbox[0] <= 32;
     CUtensorMap tms[2];
-    int rc = mq_make_maps(g, img_il, c, tms);
+    memset(tms, 0, sizeof(tms));
+    int rc = mq_make_maps(g, img_il, c, tms, P.cls0_pm != 0);
     if (rc) return rc;
     return mq_march(g, c, P, tms, angle_lo, angle_hi, st);
 }

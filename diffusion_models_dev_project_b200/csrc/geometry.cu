@@ -213,6 +213,7 @@ extern "C" int scd_set_tuning(scd_geom_t *g, const char *key, int value)
     else if (!strcmp(key, "fp_plan")) g->tune_fp_plan = value;
     else if (!strcmp(key, "fp_source")) g->tune_fp_source = value;
     else if (!strcmp(key, "fp_plan_cost")) g->tune_fp_plan_cost = value;
+    else if (!strcmp(key, "fp_cls0")) g->tune_fp_cls0 = value;
     else if (!strcmp(key, "bp_tile")) g->tune_bp_tile = value;
     else if (!strcmp(key, "bp_share")) g->tune_bp_share = value;
     else if (!strcmp(key, "bp_rows")) {

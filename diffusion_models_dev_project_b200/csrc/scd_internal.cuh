@@ -136,6 +136,7 @@ struct scd_geom {
     // tuning overrides (0 = heuristic)
     int tune_fp_samples, tune_fp_angles, tune_fp_rows, tune_fp_threads, tune_fp_nbuf, tune_fp_cluster, tune_fp_plan, tune_fp_plan_cost;
     int tune_bp_tile, tune_bp_share, tune_bp_rows;
+    int tune_fp_cls0;     // 1: class-0 strips pixel-major through tensor copies (like class 1) instead of bulk rows
     int tune_fp_source;   // 1: force the packed-copy path of the projector (A/B runs, tests)
     // sample-interleaved sinogram rows (bp_tile.cu): il_padl zero bins, n_det bins, zero bins up to il_nb
     int il_padl, il_nb;

@@ -257,7 +257,8 @@ void    scd_launch_count_reset(void);
 /* Override launch heuristics (tuning / tests).  key is one of
  * "fp_samples" (samples interleaved per pixel/bin: 1,2,4,8,16), "fp_angles", "fp_rows",
  * "fp_threads", "fp_nbuf", "fp_cluster", "fp_plan", "fp_source" (1 = packed copy + 1-D bulk copies for every
- * batch size instead of tensor copies from the interleaved image), "bp_tile", "bp_share" (1 = plain
+ * batch size instead of tensor copies from the interleaved image), "fp_cls0" (class-0 strips pixel-major through
+ * tensor copies: 1 = always, 2 = never), "fp_plan_cost" (fixed cost of a unit in the unit plan, percent of one angle), "bp_tile", "bp_share" (1 = plain
  * march, no tap sharing between the pixels of a column pair), "bp_rows" (rows in use per tile; 1 = always the
  * full tile); value 0
  * restores the heuristic.  Not thread-safe; intended for benchmarks.         */

@@ -81,7 +81,8 @@ def test_fp_bp_other_shapes(im_shape, num_angles):
                                   dict(fp_samples=8, bp_tile=32), dict(fp_samples=8, bp_tile=16), dict(fp_samples=8, bp_tile=8), dict(fp_samples=16, bp_tile=8), dict(fp_samples=16),
                                   dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_threads=768), dict(fp_samples=8, fp_angles=3, fp_rows=8, fp_threads=768, fp_cluster=2), dict(fp_samples=4, fp_threads=768),
                                   dict(fp_samples=4, bp_tile=16), dict(fp_samples=2, bp_tile=32),
-                                  dict(fp_samples=4, fp_source=1), dict(fp_samples=8, fp_source=1, fp_cluster=2), dict(fp_samples=16, fp_source=1, fp_rows=2)])
+                                  dict(fp_samples=4, fp_source=1), dict(fp_samples=8, fp_source=1, fp_cluster=2), dict(fp_samples=16, fp_source=1, fp_rows=2),
+                                  dict(fp_samples=4, fp_cls0=1), dict(fp_samples=8, fp_cls0=2), dict(fp_samples=16, fp_cls0=1, fp_rows=2), dict(fp_samples=16, fp_cls0=1, fp_cluster=2)])
 def test_tuning_variants_agree(tune):
     """Every template instantiation (samples per thread, rays per thread, tile shape) computes the same thing."""
     geom = O.OracleGeometry((96, 96), 20)

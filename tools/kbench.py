@@ -48,7 +48,7 @@ def main():
     nbytes = 4 * (a.im * a.im + rt.obs_shape[0] * rt.obs_shape[1]) * a.batch
 
     def run(tune):
-        keys = ['fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'fp_plan_cost', 'fp_source', 'bp_tile', 'bp_share', 'bp_rows']
+        keys = ['fp_samples', 'fp_angles', 'fp_rows', 'fp_threads', 'fp_nbuf', 'fp_cluster', 'fp_plan', 'fp_plan_cost', 'fp_source', 'fp_cls0', 'bp_tile', 'bp_share', 'bp_rows']
         rt.set_tuning(dev, **{k: tune.get(k, 0) for k in keys})
         if a.kernel == 'fp':
             fn = lambda: rt._fp(x)          # noqa: E731
