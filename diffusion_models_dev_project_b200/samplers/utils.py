@@ -182,8 +182,12 @@ class _AdaptGraph:
 
     @staticmethod
     def make_key(loss_fn, x, rhs, lr, gamma, n_iter, dc_type):
-        return (id(loss_fn), tuple(x.shape), x.device, None if rhs is None else tuple(rhs.shape), float(lr),
-                float(gamma), int(n_iter), dc_type)
+        # the captured graph holds the observation by address: a loss object that is re-used with another
+        # observation (or an address recycled after garbage collection) must not hit a stale graph
+        obs = loss_fn.observation
+        return (id(loss_fn), obs.data_ptr(), obs._version, tuple(obs.shape), loss_fn.tv_penalty, id(loss_fn.ray_trafo),
+                tuple(x.shape), x.device, None if rhs is None else tuple(rhs.shape), float(lr), float(gamma), int(n_iter),
+                dc_type)
 
     def reset(self):
         with torch.no_grad():

@@ -48,6 +48,9 @@ def parse():
     p.add_argument('--tv_penalty', default=1e-6)
     p.add_argument('--add_cg', action='store_true')
     p.add_argument('--dc_type', default='cg', choices=['cg', 'gd', 'none'])
+    p.add_argument('--adapt_cuda_graph', action='store_true',
+                   help='adapted mode: capture one Adam step (score model, scd_adapt_fwd / scd_adapt_bwd, optimizer) in a '
+                        'CUDA graph and replay it')
     # synthetic set-up
     p.add_argument('--im_size', type=int, default=256)
     p.add_argument('--num_angles', type=int, default=60)

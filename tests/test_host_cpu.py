@@ -504,3 +504,28 @@ def test_oracle_fbp_recipe():
     rec = O.fbp(geom, O.fp(geom, x))
     assert rel_l2(rec, x) < 0.06
     assert abs(rec[0, 32, 32] - 1.0) < 0.02
+
+
+def test_adaptation_loss_object_and_fused_objective_gate():
+    """AdaptationLoss (the loss closure of get_standard_adapted_sampler as an object) evaluates the reference's
+    expression; the fused objective only applies to the CUDA operator -- on CPU `_adapt` takes the tensor path."""
+    from diffusion_models_dev_project_b200.samplers.adaptation import (AdaptationLoss, adapt_objective,
+                                                                       adapt_objective_applies)
+    from diffusion_models_dev_project_b200.samplers.utils import _AdaptGraph
+    rt = _MatrixTrafo()
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(2, 1, 6, 5, generator=g)
+    y = torch.rand(2, 1, 4, 7, generator=g)
+    loss = AdaptationLoss(y, rt, 1e-2)
+    ref = torch.mean((rt(x) - y).pow(2)) + 1e-2 * pkg.tv_loss(x)
+    assert torch.equal(loss(x=x), ref) and torch.equal(loss(x), ref)
+    sde = pkg.DDPM()
+    assert not adapt_objective_applies(x, None, loss, sde, 'cg')                    # generic operator, CPU tensors
+    assert adapt_objective(x.clone().requires_grad_(True), x, torch.ones(2), None, loss, sde, 0.1, 1, 'cg') is None
+    assert not adapt_objective_applies(x, None, lambda x: x.sum(), sde, 'cg')
+    # the graph cache key follows the observation (address and version), the operator and every scalar
+    k1 = _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 1, 'cg')
+    assert k1 == _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 1, 'cg')
+    y.add_(1.0)
+    assert k1 != _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 1, 'cg')
+    assert _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 2, 'cg') != _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 1, 'cg')
