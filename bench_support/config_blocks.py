@@ -134,7 +134,7 @@ def stack_block(dev, world, rank, im=501, angles=1200, slices=501, chunk=128, it
             out['op_ms_peer_multicast'] = _timed(lambda: shm.normal_apply(x, gamma), iters, dev, world)
         del shm
     out['op_ms'] = min(v for v in (out['op_ms_nccl'], out.get('op_ms_peer'), out.get('op_ms_peer_multicast')) if v is not None)
-    out['exposed_collective_ms'] = max(0.0, out['op_ms_nccl'] - out['op_local_ms'])
+    out['exposed_collective_ms'] = max(0.0, out['op_ms_nccl'] - out['op_local_ms']) if world > 1 else 0.0
     out['overlap_hidden_ms'] = max(0.0, out['allreduce_alone_ms'] - out['exposed_collective_ms'])
     bytes_rank = 4 * (im * im + (hi - lo) * n_det) * slices       # per-rank algorithmic bytes of A (and of A*)
     out['A_GBps_per_rank'] = bytes_rank / (out['A_ms'] * 1e-3) / 1e9
