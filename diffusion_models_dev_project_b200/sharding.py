@@ -6,7 +6,8 @@ Two cases (the reference itself is single-process, single-
   reductions are per sample, reference src/utils/cg.py:22,27,33), so the batch is split into
   contiguous shards and no collective touches the data path: :func:`shard_range`.
 
-* **One large slice stack, angle-sharded** -- rank r owns the angles ``[lo_r, hi_r)``.
+* **One large slice stack, angle-sharded** -- rank r owns the contiguous angles ``[lo_r, hi_r)``, chosen so that
+  every rank carries the same projector + backprojector cost (:func:`angle_cost_ranges`).
   ``A``: each rank computes only its sinogram rows (no communication; the other rows of the
   returned tensor are zero).  ``A*``: each rank backprojects its rows into a full-size partial
   image stack and the partials are summed with an all-reduce (NCCL over NVLink on the GPU box).
@@ -38,6 +39,32 @@ def shard_range(n: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def angle_cost_ranges(angles, world: int, fp_weight: float = 1.75):
+    """Contiguous angle ranges ``[(lo, hi)] * world`` of (nearly) equal COST instead of equal count.
+
+    The ray-driven projector skips the part of every ray that misses the image, so an angle costs it in proportion
+    to ``max(|cos phi|, |sin phi|)`` (the number of (row, ray) pairs inside the square): angles near the axes are
+    ~40 % dearer than angles near the diagonals.  The pixel-driven backprojector costs the same for every angle.
+    ``cost_i = fp_weight * max(|cos|, |sin|) / 0.9 + 1`` with ``fp_weight`` = time of A over time of A* per angle
+    (measured ~1.75 on the 501^2 stack).  With equal counts over 8 ranks the two outer and the two middle ranks carry
+    the dear angles and set the time of A for everyone."""
+    import numpy as np
+    a = np.asarray(angles, dtype=np.float64)
+    n = len(a)
+    if world <= 1 or n < world:
+        return [shard_range(n, r, world) for r in range(world)]
+    cost = fp_weight * np.maximum(np.abs(np.cos(a)), np.abs(np.sin(a))) / 0.9 + 1.0
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    bounds = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        k = int(np.searchsorted(cum, target))
+        k = k if abs(cum[k] - target) <= abs(cum[k - 1] - target) else k - 1
+        bounds.append(min(max(k, bounds[-1] + 1), n - (world - r)))          # every rank keeps at least one angle
+    bounds.append(n)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
 class AngleShardedRayTrafo:
     """Angle-sharded view of a ray transform.
 
@@ -52,7 +79,7 @@ class AngleShardedRayTrafo:
     Inference-only: the sharded operators do not record autograd graphs and raise if an input requires grad.
     """
 
-    def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl', multicast=None):
+    def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl', multicast=None, balance: str = 'cost'):
         if reduce not in ('nccl', 'peer'):
             raise ValueError("reduce must be 'nccl' or 'peer'")
         self.reduce = reduce
@@ -66,7 +93,11 @@ class AngleShardedRayTrafo:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.im_shape = base.im_shape
         self.obs_shape = base.obs_shape
-        self.angle_range = shard_range(base.obs_shape[0], self.rank, self.world)
+        # 'cost': ranges of equal projector + backprojector cost (angle_cost_ranges); 'count': equal angle counts
+        if balance not in ('cost', 'count'):
+            raise ValueError("balance must be 'cost' or 'count'")
+        self.angle_range = angle_cost_ranges(base.angles, self.world)[self.rank] if balance == 'cost' \
+            else shard_range(base.obs_shape[0], self.rank, self.world)
         self.chunk = int(chunk)
         self._comm_stream = None
 
@@ -98,6 +129,16 @@ class AngleShardedRayTrafo:
             raise RuntimeError('AngleShardedRayTrafo.%s does not support autograd (inference-only view): call it '
                                'under torch.no_grad() or detach the input' % what)
 
+    def _chunk_bounds(self, n: int):
+        """Slice chunks ``[(lo, hi)]``: ``chunk`` slices each, the last one split in two when a collective follows --
+        the reduction of the final chunk is the only one with nothing to hide behind, so it is kept short."""
+        bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
+        if self.world > 1 and bounds and bounds[-1][1] - bounds[-1][0] >= 32:
+            lo, hi = bounds.pop()
+            mid = lo + (hi - lo + 1) // 2
+            bounds += [(lo, mid), (mid, hi)]
+        return bounds
+
     def _reduce_chunks(self, produce, n: int, out: Tensor) -> Tensor:
         """``out[c] = all_reduce(produce(c))`` over slice chunks, communication of chunk c overlapping the
         computation of chunk c+1 (side stream on CUDA).  ``produce(lo, hi, dst)`` writes this rank's partial of
@@ -111,15 +152,15 @@ class AngleShardedRayTrafo:
                 dst.copy_(res)
             return dst
         if self.world == 1:
-            for lo in range(0, n, self.chunk):
-                make(lo, min(n, lo + self.chunk))
+            for lo, hi in self._chunk_bounds(n):
+                make(lo, hi)
             return out
         on_cuda = out.is_cuda
         if on_cuda and self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream(device=out.device)
         pending = []
-        for lo in range(0, n, self.chunk):
-            part = make(lo, min(n, lo + self.chunk))
+        for lo, hi in self._chunk_bounds(n):
+            part = make(lo, hi)
             if on_cuda:
                 ready = torch.cuda.Event()
                 ready.record(torch.cuda.current_stream(out.device))
@@ -254,8 +295,7 @@ class _PeerReduce:
         self.calls += 1
         result, result_ptrs, result_mc = self.results[which], self.result_ptrs[which], self.result_mc[which]
         landed = []                                              # event: barrier after chunk c's stores
-        for c, lo in enumerate(range(0, n, m)):
-            hi = min(n, lo + m)
+        for c, (lo, hi) in enumerate(sh._chunk_bounds(n)):      # chunks of at most m slices (the staging slot size)
             buf = c % self.NBUF
             if c >= self.NBUF:
                 # the owners have reduced chunk c - NBUF (their reduction precedes their barrier of chunk

@@ -27,9 +27,11 @@ def _worker(rank, world, port, tmp):
         from diffusion_models_dev_project_b200.sharding import AngleShardedRayTrafo, shard_range
         torch.set_grad_enabled(False)
         rt = pkg.B200RayTrafo((96, 96), 30)
+        from diffusion_models_dev_project_b200.sharding import angle_cost_ranges
         sh = AngleShardedRayTrafo(rt, chunk=3)
         lo, hi = sh.angle_range
-        assert (lo, hi) == shard_range(30, rank, world)
+        assert (lo, hi) == angle_cost_ranges(rt.angles, world)[rank]
+        assert AngleShardedRayTrafo(rt, chunk=3, balance='count').angle_range == shard_range(30, rank, world)
         gen = torch.Generator(device=dev).manual_seed(0)          # replicated vectors
         x = torch.rand(7, 1, 96, 96, device=dev, generator=gen)
         y = torch.randn(7, 1, *rt.obs_shape, device=dev, generator=gen)

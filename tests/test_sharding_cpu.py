@@ -55,7 +55,8 @@ def _worker(rank, world, port, tmp):
         geom = O.OracleGeometry((24, 24), 10)
         base = OracleBase(geom)
         sh = AngleShardedRayTrafo(base, chunk=2)
-        assert sh.angle_range == shard_range(10, rank, world)
+        from diffusion_models_dev_project_b200.sharding import angle_cost_ranges
+        assert sh.angle_range == angle_cost_ranges(geom.angles, world)[rank]
         g = torch.Generator().manual_seed(0)            # same data on every rank (replicated vectors)
         x = torch.rand(5, 1, 24, 24, generator=g)
         y = torch.randn(5, 1, *geom.obs_shape, generator=g)
@@ -121,3 +122,23 @@ def test_sharded_view_refuses_autograd():
         out = sh.normal_apply(x, 0.1)
     ref = x.detach() + 0.1 * OracleBase(geom)._bp(OracleBase(geom)._fp(x.detach()), geom.adj_scale)
     assert rel_l2(out.numpy(), ref.numpy()) < 1e-6
+
+
+def test_angle_cost_ranges_partition_and_balance():
+    """Cost-balanced contiguous angle ranges: a partition of all angles, every rank non-empty, per-rank cost within
+    one angle's cost of the mean; the dear angles (near the axes) end up in shorter ranges."""
+    from diffusion_models_dev_project_b200.sharding import angle_cost_ranges
+    for n in (8, 30, 60, 1200):
+        ang = (np.arange(n) + 0.5) * np.pi / n
+        cost = 1.75 * np.maximum(np.abs(np.cos(ang)), np.abs(np.sin(ang))) / 0.9 + 1.0
+        for world in (1, 2, 3, 4, 8):
+            parts = angle_cost_ranges(ang, world)
+            assert parts[0][0] == 0 and parts[-1][1] == n and len(parts) == world
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+            assert all(hi > lo for lo, hi in parts)
+            per = [cost[lo:hi].sum() for lo, hi in parts]
+            assert max(per) - cost.sum() / world <= cost.max() + 1e-9
+    parts = angle_cost_ranges((np.arange(1200) + 0.5) * np.pi / 1200, 8)
+    sizes = [hi - lo for lo, hi in parts]
+    assert sizes[0] < sizes[1] and sizes[3] < sizes[2] and sizes == sizes[::-1]        # 142 / 158 instead of 150 / 150
+    assert angle_cost_ranges(np.zeros(3), 8)[7] == shard_range(3, 7, 8)                  # fewer angles than ranks
