@@ -177,6 +177,28 @@ __device__ __forceinline__ void bq_tap3(float (&p)[4], float4 t0, float4 t1, flo
     p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
 }
 
+// Pair march of two pixels of a column whose detector coordinates satisfy zlo <= zhi < zlo + 1: their four taps lie
+// in the three consecutive bins starting at floor(zlo) -- 3 loads instead of 4.  The lower pixel takes (1-w, w) on bins
+// 0, 1; the upper one (1-w, w, 0) or (0, 1-w, w).  The product with the exact zero changes nothing and the real taps
+// are added in the order of the plain march: bit-identical to it.
+template <int V, int SB>
+__device__ __forceinline__ void bq_pair(float (&acc_lo)[V], float (&acc_hi)[V], float zlo, float zhi, unsigned seg)
+{
+    typedef BqVec<V> LD;
+    typedef typename LD::T VT;
+    const float tlo = __fadd_rd(zlo, BQ_MAGIC), thi = __fadd_rd(zhi, BQ_MAGIC);
+    const float wlo = zlo - (tlo - BQ_MAGIC), whi = zhi - (thi - BQ_MAGIC);
+    const int ilo = __float_as_int(tlo), ihi = __float_as_int(thi);
+    const unsigned ad = seg + (unsigned)ilo * (unsigned)(SB * 4);
+    const VT b0 = LD::template ld<0>(ad);
+    const VT b1 = LD::template ld<SB * 4>(ad);
+    const VT b2 = LD::template ld<2 * SB * 4>(ad);
+    bq_tap(acc_lo, b0, b1, 1.0f - wlo, wlo);
+    const bool s = ihi != ilo;                                   // the upper pixel's left tap is bin 1
+    const float uh = 1.0f - whi;
+    bq_tap3(acc_hi, b0, b1, b2, s ? 0.0f : uh, s ? uh : whi, s ? whi : 0.0f);
+}
+
 // V samples per lane, LPR lanes per pixel (SB = V*LPR), PPT pixels per thread; IL: the epilogue's images are
 // sample-interleaved (il images)
 template <int V, int LPR, int PPT, bool IL>
@@ -324,21 +346,17 @@ bp_tile_kernel(const BqParams P)
                     // weighs the three bins with (1-w, w, 0) or (0, 1-w, w); the products with an exact
                     // zero change nothing, the two real taps are added in the same order as in the
                     // plain march, so the results are bit-identical to it.
+                    // The sign of ci is the same for the whole angle (warp-uniform), so it is known which pixel
+                    // of the pair has the smaller detector coordinate: that one always weighs (1-w, w) on the first
+                    // two bins -- two taps, no selects -- and only the other one needs the three-bin form.
+                    if (cs.x >= 0.0f) {
 #pragma unroll
-                    for (int m = 0; m + 1 < PPT; m += 2) {
-                        const float z0 = fmaf(kyf[m], cs.x, vb), z1 = fmaf(kyf[m + 1], cs.x, vb);
-                        const float t0 = __fadd_rd(z0, BQ_MAGIC), t1 = __fadd_rd(z1, BQ_MAGIC);
-                        const float w0 = z0 - (t0 - BQ_MAGIC), w1 = z1 - (t1 - BQ_MAGIC);
-                        const int i0 = __float_as_int(t0), i1 = __float_as_int(t1);
-                        const int ib = min(i0, i1);
-                        const unsigned ad = seg + (unsigned)ib * (unsigned)(SB * 4);
-                        const VT b0 = LD::template ld<0>(ad);
-                        const VT b1 = LD::template ld<SB * 4>(ad);
-                        const VT b2 = LD::template ld<2 * SB * 4>(ad);
-                        const bool s0 = i0 != ib, s1 = i1 != ib;          // left tap of the pixel is bin 1
-                        const float u0 = 1.0f - w0, u1 = 1.0f - w1;
-                        bq_tap3(acc[m], b0, b1, b2, s0 ? 0.0f : u0, s0 ? u0 : w0, s0 ? w0 : 0.0f);
-                        bq_tap3(acc[m + 1], b0, b1, b2, s1 ? 0.0f : u1, s1 ? u1 : w1, s1 ? w1 : 0.0f);
+                        for (int m = 0; m + 1 < PPT; m += 2)
+                            bq_pair<V, SB>(acc[m], acc[m + 1], fmaf(kyf[m], cs.x, vb), fmaf(kyf[m + 1], cs.x, vb), seg);
+                    } else {
+#pragma unroll
+                        for (int m = 0; m + 1 < PPT; m += 2)
+                            bq_pair<V, SB>(acc[m + 1], acc[m], fmaf(kyf[m + 1], cs.x, vb), fmaf(kyf[m], cs.x, vb), seg);
                     }
                     continue;
                 }

@@ -351,3 +351,18 @@ def test_interleaved_image_path(im_shape, num_angles, batch):
     assert rel_l2(z2.cpu().numpy(), (0.5 * z + 2.0 * x).cpu().numpy()) < 1e-6
     with pytest.raises(ValueError):
         rt._img_il(x[:2])
+
+
+@pytest.mark.parametrize('im_shape,num_angles,batch', [((256, 256), 60, 16), ((256, 256), 60, 256), ((501, 501), 40, 20), ((96, 70), 13, 6)])
+def test_pair_march_is_bit_identical_to_the_plain_march(im_shape, num_angles, batch):
+    """bp_tile's pair march (3 loads for the 4 taps of a column pair; the lower pixel of the pair -- known from the
+    sign of cos(phi), uniform per angle -- takes two taps, the upper one the three-bin form with an exact zero weight)
+    against the plain two-taps-per-pixel march (tuning bp_share = 1): same bits."""
+    rt = _rt(im_shape, num_angles)
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    y = torch.randn(batch, 1, *rt.obs_shape, device='cuda', generator=gen)
+    z = rt.trafo_adjoint(y)
+    rt.set_tuning('cuda', bp_share=1)
+    z_plain = rt.trafo_adjoint(y)
+    rt.set_tuning('cuda', bp_share=0)
+    assert torch.equal(z, z_plain)
