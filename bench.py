@@ -8,7 +8,7 @@ full-size guided-diffusion UNet as the (PyTorch) score caller, synthetic disk-el
 random-init weights.
 
 One bench *step* = one reverse-diffusion step of the whole batch: score call, then the hot path
-(Tweedie -> rhs -> CG(5): 6 A + 6 A* + vector updates -> DDIM).  A sample needs 100 of them, so
+(Tweedie -> rhs -> CG(5): 6 A + 6 A* + vector updates -> DDIM: 19 launches).  A sample needs 100 of them, so
     value [samples/s] = n_gpus * batch / (100 * seconds_per_step).
 Multi-GPU: one process per GPU, the sample batch is sharded, no data-path collective (weak scaling).
 
@@ -482,10 +482,10 @@ def run_b200(args):
                     'algorithmic_bytes_per_launch': BYTES[dom] * B, 'launch_ms': sweep_small[dom]['ms'],
                     'shared_memory_pipe_frac_ncu': pipe,
                     'note': 'A/A* are bound by the shared-memory pipe (8 B per tap pair and sample), not HBM: '
-                            'DESIGN.md section 4; large-batch figures in kernels_b%d.  traffic is the DRAM '
-                            'traffic under ncu, which flushes the caches before every launch: it is the packed '
-                            'image (2.06 x the images) that the preceding pack pass leaves in L2 when the '
-                            'kernels run back to back' % args.kernel_batch}
+                            'DESIGN.md section 4; large-batch figures in kernels_b%d.  The kernel is timed on a '
+                            'sample-interleaved image, the form it has inside CG (scd_fp_ilimg: one launch, no packed copy); '
+                            'traffic is its DRAM traffic under ncu (cold caches): the image once, the sinogram once'
+                            % args.kernel_batch}
         line = {
             'metric': 'SCD samples/sec at 256^2', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
