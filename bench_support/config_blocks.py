@@ -256,5 +256,21 @@ def adapted_block(dev, world, rank, steps=2, warm=1, full_unet=True):
                         'samples_per_s_full_unet': world * 1e3 / (ms_full * args.num_steps),
                         'path_share_of_step': ms_path / ms_full, 'finite': ok1 and ok2})
             del score, full
+            # the same with the whole Adam step -- UNet forward + backward included -- captured in a CUDA graph: possible
+            # because scd_adapt_fwd / scd_adapt_bwd allocate nothing and never synchronise
+            try:
+                torch.manual_seed(0)
+                score = aapm_unet().to(dev).eval()
+                a4 = copy.copy(args)
+                a4.adapt_cuda_graph = True
+                fullg = pkg.get_standard_adapted_sampler(args=a4, config=config, score=score, sde=sde, ray_trafo=rt,
+                                                         observation=y, device=dev, lora_inject_fn=inject_trainable_lora)
+                ms_fullg, _, ok4 = time_steps(fullg)
+                out.update({'ms_per_reverse_step_full_unet_cuda_graph': ms_fullg,
+                            'samples_per_s_full_unet_cuda_graph': world * 1e3 / (ms_fullg * args.num_steps),
+                            'finite': out['finite'] and ok4})
+                del score, fullg
+            except Exception as e:                      # capture of a caller's model is best effort
+                out['full_unet_cuda_graph_unavailable'] = '%s: %s' % (type(e).__name__, str(e)[:200])
     torch.cuda.empty_cache()
     return out
