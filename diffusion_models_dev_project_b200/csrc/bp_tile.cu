@@ -623,8 +623,7 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     }
     if (c.grid.z > 65535) { scd_set_error("scd_bp: batch too large"); return SCD_E_INVALID; }
     if (c.smem > (size_t)g->smem_optin) { scd_set_error("scd_bp: angle table does not fit in shared memory"); return SCD_E_INVALID; }
-    BqParams P;
-    memset(&P, 0, sizeof(P));
+    BqParams P = BqParams();                       // value-initialised (the epilogue carries default member initialisers)
     P.sino_il = sino_il; P.out = out; P.bp = g->d_bp;
     P.n0 = g->n0; P.n1 = g->n1; P.n_angles = g->n_angles; P.n_det = g->n_det; P.batch = batch;
     P.angle_lo = angle_lo; P.angle_hi = angle_hi; P.SEG = c.SEG; P.AC = c.AC; P.nbuf = c.nbuf;
