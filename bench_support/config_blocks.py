@@ -48,7 +48,7 @@ def _timed(fn, iters, dev, world, warm=2):
 
 
 # --------------------------------------------------------------------------- config 4 ---
-def stack_block(dev, world, rank, im=501, angles=1200, slices=501, chunk=128, iters=3, check=2, gamma=0.01):
+def stack_block(dev, world, rank, im=501, angles=1200, slices=501, chunk=256, iters=3, check=2, gamma=0.01):
     import diffusion_models_dev_project_b200 as pkg
     from diffusion_models_dev_project_b200.sharding import AngleShardedRayTrafo
     rt = pkg.B200RayTrafo((im, im), angles)

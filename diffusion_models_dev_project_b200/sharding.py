@@ -79,7 +79,7 @@ class AngleShardedRayTrafo:
     Inference-only: the sharded operators do not record autograd graphs and raise if an input requires grad.
     """
 
-    def __init__(self, base, group=None, chunk: int = 128, reduce: str = 'nccl', multicast=None, balance: str = 'cost'):
+    def __init__(self, base, group=None, chunk: int = 256, reduce: str = 'nccl', multicast=None, balance: str = 'cost'):
         if reduce not in ('nccl', 'peer'):
             raise ValueError("reduce must be 'nccl' or 'peer'")
         self.reduce = reduce
@@ -130,9 +130,11 @@ class AngleShardedRayTrafo:
                                'under torch.no_grad() or detach the input' % what)
 
     def _chunk_bounds(self, n: int):
-        """Slice chunks ``[(lo, hi)]`` of ``chunk`` slices.  (Splitting the last chunk in two to shorten the only
-        reduction with nothing to hide behind was measured on 8 GPUs: the smaller launches cost the projector what
-        the collective gains -- exposed part 0.69 -> 0.99 ms.)"""
+        """Slice chunks ``[(lo, hi)]`` of ``chunk`` slices.  The projector and backprojector like large batches more
+        than the pipeline likes many chunks: 501 slices on 8 GPUs, `op` with chunks of 128 / 167 / 251 slices: 12.85 /
+        13.18 / 12.67 ms (NCCL), 12.84 / 12.65 / 12.36 ms (peer-staged, multicast store) -- hence the default of 256.
+        (Splitting the last chunk in two to shorten the only reduction with nothing to hide behind was also measured:
+        the smaller launches cost the projector what the collective gains.)"""
         return [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
 
     def _reduce_chunks(self, produce, n: int, out: Tensor) -> Tensor:

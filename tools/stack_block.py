@@ -1,4 +1,5 @@
-"""Config 4 block of bench.py on its own (all ranks): python -m torch.distributed.run ... tools/stack_block.py"""
+"""Config 4 block of bench.py on its own (all ranks):
+    python -m torch.distributed.run ... tools/stack_block.py [repeats] [chunk sizes, comma separated]"""
 import json, os, sys
 import torch
 import torch.distributed as dist
@@ -11,10 +12,12 @@ dev = torch.device('cuda', local)
 if world > 1:
     dist.init_process_group('nccl', device_id=dev)
 torch.set_grad_enabled(False)
+chunks = [int(c) for c in sys.argv[2].split(',')] if len(sys.argv) > 2 else [128]
 for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 1):
-    out = CB.stack_block(dev, world, rank)
-    if rank == 0:
-        print(json.dumps(out))
+    for chunk in chunks:
+        out = CB.stack_block(dev, world, rank, chunk=chunk)
+        if rank == 0:
+            print(json.dumps(out))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
