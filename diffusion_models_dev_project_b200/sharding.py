@@ -130,12 +130,16 @@ class AngleShardedRayTrafo:
                                'under torch.no_grad() or detach the input' % what)
 
     def _chunk_bounds(self, n: int):
-        """Slice chunks ``[(lo, hi)]`` of ``chunk`` slices.  The projector and backprojector like large batches more
+        """Slice chunks ``[(lo, hi)]`` of at most ``chunk`` slices, equal in size.  The projector and backprojector like large batches more
         than the pipeline likes many chunks: 501 slices on 8 GPUs, `op` with chunks of 128 / 167 / 251 slices: 12.85 /
         13.18 / 12.67 ms (NCCL), 12.84 / 12.65 / 12.36 ms (peer-staged, multicast store) -- hence the default of 256.
         (Splitting the last chunk in two to shorten the only reduction with nothing to hide behind was also measured:
         the smaller launches cost the projector what the collective gains.)"""
-        return [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
+        if n <= 0:
+            return []
+        k = -(-n // self.chunk)                        # number of chunks; sizes levelled (501 -> 251 + 250, not 256 + 245)
+        size = -(-n // k)
+        return [(lo, min(n, lo + size)) for lo in range(0, n, size)]
 
     def _reduce_chunks(self, produce, n: int, out: Tensor) -> Tensor:
         """``out[c] = all_reduce(produce(c))`` over slice chunks, communication of chunk c overlapping the
