@@ -130,6 +130,9 @@ class _AdaptObjectiveFn(torch.autograd.Function):
         from .. import _lib
         lib = _lib.load()
         rt = ctx.rt
+        if ctx.work is None:
+            raise RuntimeError('the adaptation objective was already differentiated: its saved state lives in a workspace '
+                               'that is released by the first backward pass (retain_graph is not supported)')
         dev = ctx.t.device
         h = rt._handle(dev)
         gamma, n_iter, dc_code, lam = ctx.args

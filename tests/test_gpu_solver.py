@@ -425,5 +425,12 @@ def test_fused_adaptation_objective_matches_the_tensor_path(dc_type, n_iter, bat
     (3.0 * lb).backward()
     assert abs(float(la) - float(lb)) / abs(float(lb)) < 1e-5, (float(la), float(lb))
     assert rel_l2(sa.grad.cpu().numpy(), sb.grad.cpu().numpy()) < 1e-4
+    # the saved state is released by the first backward pass: a second one is refused, not a use-after-free
+    if batch == 1 and dc_type == 'cg' and n_iter == 1:
+        sc = s0.clone().requires_grad_(True)
+        lc = adapt_objective(sc, x, t, rhs, loss_fn, sde, gamma, n_iter, dc_type)
+        lc.backward(retain_graph=True)
+        with pytest.raises(RuntimeError, match='already differentiated'):
+            lc.backward()
     # no fused path for other losses / operators: the caller falls back to the tensor expression
     assert adapt_objective(sa, x, t, rhs, lambda x: x.sum(), sde, gamma, n_iter, dc_type) is None
