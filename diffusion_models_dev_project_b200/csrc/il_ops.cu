@@ -75,17 +75,22 @@ il_pack_kernel(const float *__restrict__ a_user, float *__restrict__ a_il, const
     const int tw = min(IL_TP, n1 - K1);
     const size_t isz = (size_t)n0 * n1;
     const int px = threadIdx.x & (IL_TP - 1), ps = threadIdx.x >> 7;       // 2 samples per round
-#pragma unroll 4
-    for (int s0 = 0; s0 < SB; s0 += 2) {
-        const int s = s0 + ps, b = grp * SB + s;
-        float va = 0.f, vb = 0.f;
+    // all loads of the thread in flight before the first one is consumed (the kernel is pure data movement)
+    float va[SB / 2], vb[SB / 2];
+#pragma unroll
+    for (int i = 0; i < SB / 2; ++i) {
+        const int b = grp * SB + 2 * i + ps;
+        va[i] = vb[i] = 0.f;
         if (b < batch && px < tw) {
             const size_t o = (size_t)b * isz + (size_t)k0 * n1 + K1 + px;
-            va = __ldg(a_user + o);
-            if (b_user) vb = __ldg(b_user + o);
+            va[i] = __ldg(a_user + o);
+            if (b_user) vb[i] = __ldg(b_user + o);
         }
-        ta[s * ST + px] = va;
-        tb[s * ST + px] = vb;
+    }
+#pragma unroll
+    for (int i = 0; i < SB / 2; ++i) {
+        ta[(2 * i + ps) * ST + px] = va[i];
+        if (b_user) tb[(2 * i + ps) * ST + px] = vb[i];
     }
     __syncthreads();
     const size_t row_off = ((size_t)grp * n0 + k0) * n1;
