@@ -138,8 +138,7 @@ class AngleShardedRayTrafo:
         if n <= 0:
             return []
         k = -(-n // self.chunk)                        # number of chunks; sizes levelled (501 -> 251 + 250, not 256 + 245)
-        size = -(-n // k)
-        return [(lo, min(n, lo + size)) for lo in range(0, n, size)]
+        return [shard_range(n, i, k) for i in range(k)]
 
     def _reduce_chunks(self, produce, n: int, out: Tensor) -> Tensor:
         """``out[c] = all_reduce(produce(c))`` over slice chunks, communication of chunk c overlapping the

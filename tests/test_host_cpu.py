@@ -529,3 +529,17 @@ def test_adaptation_loss_object_and_fused_objective_gate():
     y.add_(1.0)
     assert k1 != _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 1, 'cg')
     assert _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 2, 'cg') != _AdaptGraph.make_key(loss, x, x, 1e-3, 0.1, 1, 'cg')
+
+
+def test_bench_build_id_and_reference_arm_helpers():
+    """bench.py records which library it measured (sha256 of the .so and of its sources) and how many host threads the
+    CPU arm used."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    bid = bench.build_id()
+    assert set(bid) == {'lib_sha16', 'src_sha16', 'stale'} and len(bid['lib_sha16']) == 16 and bid['stale'] is False
+    assert bench.host_cores() >= 1
+    pairs = bench.time_pairs()
+    assert len(pairs) == 100 and pairs[0] == (990, 980) and pairs[-1] == (0, -1)

@@ -142,3 +142,14 @@ def test_angle_cost_ranges_partition_and_balance():
     sizes = [hi - lo for lo, hi in parts]
     assert sizes[0] < sizes[1] and sizes[3] < sizes[2] and sizes == sizes[::-1]        # 142 / 158 instead of 150 / 150
     assert angle_cost_ranges(np.zeros(3), 8)[7] == shard_range(3, 7, 8)                  # fewer angles than ranks
+
+
+def test_chunk_bounds_are_levelled_and_cover_the_stack():
+    geom = O.OracleGeometry((16, 16), 6)
+    for n, chunk, want in ((501, 256, [251, 250]), (501, 128, [126, 125, 125, 125]), (7, 3, [3, 3, 1]), (5, 8, [5]), (0, 4, [])):
+        sh = AngleShardedRayTrafo(OracleBase(geom), chunk=chunk)
+        b = sh._chunk_bounds(n)
+        assert [hi - lo for lo, hi in b] == want
+        assert all(hi - lo <= chunk for lo, hi in b)
+        assert (b[0][0], b[-1][1]) == (0, n) if n else b == []
+        assert all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
