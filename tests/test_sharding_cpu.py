@@ -146,7 +146,7 @@ def test_angle_cost_ranges_partition_and_balance():
 
 def test_chunk_bounds_are_levelled_and_cover_the_stack():
     geom = O.OracleGeometry((16, 16), 6)
-    for n, chunk, want in ((501, 256, [251, 250]), (501, 128, [126, 125, 125, 125]), (7, 3, [3, 3, 1]), (5, 8, [5]), (0, 4, [])):
+    for n, chunk, want in ((501, 256, [251, 250]), (501, 128, [126, 125, 125, 125]), (7, 3, [3, 2, 2]), (5, 8, [5]), (0, 4, [])):
         sh = AngleShardedRayTrafo(OracleBase(geom), chunk=chunk)
         b = sh._chunk_bounds(n)
         assert [hi - lo for lo, hi in b] == want
