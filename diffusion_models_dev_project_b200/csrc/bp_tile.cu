@@ -635,11 +635,13 @@ int scd_launch_bp_il(const scd_geom *g, const float *sino_il, float *out, int ba
     const int WY = BQ_NW / c.LPR;
     (void)WY;
     if (ep.il) {
-        if (c.V != 4 || ep.n_bands) { scd_set_error("scd_bp: interleaved images need groups of >= 4 samples and no bands"); return SCD_E_INVALID; }
+        if (c.V == 2 || ep.n_bands) { scd_set_error("scd_bp: interleaved images need groups of 1 or >= 4 samples and no bands"); return SCD_E_INVALID; }
         if (ep.mode == 1 && (!ep.add1 || !ep.out2 || (ep.beta && !ep.add2))) { scd_set_error("scd_bp: direction step needs r, p"); return SCD_E_INVALID; }
-#define BQ_CASE_IL(LL, PP) if (c.LPR == LL && c.PPT == PP) return bq_launch_t<4, LL, PP, true>(P, c, st, g->device);
+#define BQ_CASE_IL(LL, PP) if (c.V == 4 && c.LPR == LL && c.PPT == PP) return bq_launch_t<4, LL, PP, true>(P, c, st, g->device);
         BQ_CASE_IL(1, 1) BQ_CASE_IL(1, 2) BQ_CASE_IL(2, 1) BQ_CASE_IL(2, 2) BQ_CASE_IL(2, 4) BQ_CASE_IL(4, 2) BQ_CASE_IL(4, 4)
 #undef BQ_CASE_IL
+        if (c.V == 1 && c.PPT == 1) return bq_launch_t<1, 1, 1, true>(P, c, st, g->device);      // one sample per group
+        if (c.V == 1 && c.PPT == 2) return bq_launch_t<1, 1, 2, true>(P, c, st, g->device);
     }
 #define BQ_CASE(VV, LL, PP) if (c.V == VV && c.LPR == LL && c.PPT == PP) return bq_launch_t<VV, LL, PP, false>(P, c, st, g->device);
     BQ_CASE(1, 1, 1) BQ_CASE(1, 1, 2) BQ_CASE(2, 1, 1) BQ_CASE(2, 1, 2) BQ_CASE(4, 1, 1) BQ_CASE(4, 1, 2)

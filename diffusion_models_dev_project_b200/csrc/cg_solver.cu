@@ -141,17 +141,20 @@ int scd_cg_run(const scd_geom *g, const float *x_in, float *x, const float *rhs,
 }
 
 // ---- interleaved-state solve ---------------------------------------------------------------------
-// On entry the il images at L.il_x (start iterate) and L.il_b (right-hand side) are filled; on exit L.il_x holds
-// the result.
-static int cg_run_il(const scd_geom *g, const CgLayout &L, float gamma, int n_iter, int batch, char *w, cudaStream_t st)
+// x_in: start iterate (read only), x: result (may be x_in), b: right-hand side -- all il images; q, r, p, d, the
+// partial sums and beta live in the workspace.  With one sample per group (batch 1) an il image IS the reference
+// layout, so the caller's tensors are used directly and the update kernel is the reference-layout one.
+static int cg_run_il(const scd_geom *g, const CgLayout &L, const float *x_in, float *x, const float *b, float gamma,
+                     int n_iter, int batch, char *w, cudaStream_t st)
 {
-    float *q = (float *)(w + L.il_q), *x = (float *)(w + L.il_x), *r = (float *)(w + L.il_r);
-    float *p = (float *)(w + L.il_p), *d = (float *)(w + L.il_d), *b = (float *)(w + L.il_b);
+    float *q = (float *)(w + L.il_q), *r = (float *)(w + L.il_r);
+    float *p = (float *)(w + L.il_p), *d = (float *)(w + L.il_d);
     float *part = (float *)(w + L.il_part), *beta = (float *)(w + L.il_beta);
     const int ps = (int)L.part_stride;
     float *rr_a = part, *rr_b = part + (size_t)ps * batch, *pd = part + 2 * (size_t)ps * batch;
+    const int SB = scd_group_samples(g, batch);
     const int nbp = scd_bp_ctas_per_sample(g, batch);
-    const int nvec = scd_il_vec_blocks(g, batch);
+    const int nvec = SB == 1 ? scd_vec_blocks_per_sample((int64_t)L.img, batch) : scd_il_vec_blocks(g, batch);
     if (nbp > ps || nvec > ps) {
         scd_set_error("scd_cg: %d partial sums per sample exceed the workspace stride %d", std::max(nbp, nvec), ps);
         return SCD_E_INVALID;
@@ -160,10 +163,10 @@ static int cg_run_il(const scd_geom *g, const CgLayout &L, float gamma, int n_it
     const int na = g->n_angles;
     int rc;
     // r = b - x - gamma A*(A x);  rr = ||r||^2
-    if ((rc = scd_launch_fp_ilimg(g, x, nullptr, q, batch, 0, na, st, nullptr))) return rc;
+    if ((rc = scd_launch_fp_ilimg(g, x_in, nullptr, q, batch, 0, na, st, nullptr))) return rc;
     BpEpilogue e0;
     e0.il = 1; e0.mode = 0;
-    e0.c_acc = -gs; e0.add1 = x; e0.c1 = -1.f; e0.add2 = b; e0.c2 = 1.f;
+    e0.c_acc = -gs; e0.add1 = x_in; e0.c1 = -1.f; e0.add2 = b; e0.c2 = 1.f;
     e0.out2 = nullptr; e0.dot_part = rr_a; e0.dot_stride = ps; e0.dot_with_add1 = 0;
     if ((rc = scd_launch_bp_il(g, q, r, batch, 0, na, e0, st))) return rc;
     float *rr_new = rr_a, *rr_old = rr_b;          // newest ||r||^2 partials / the ones before
@@ -181,8 +184,13 @@ static int cg_run_il(const scd_geom *g, const CgLayout &L, float gamma, int n_it
         e1.beta = it > 0 ? beta : nullptr;
         e1.out2 = p; e1.dot_part = pd; e1.dot_stride = ps; e1.dot_with_add1 = 0;
         if ((rc = scd_launch_bp_il(g, q, d, batch, 0, na, e1, st))) return rc;
-        // alpha = rr/pd;  x += alpha p;  r -= alpha d;  rr' = ||r||^2
-        if ((rc = scd_launch_cg_update_xr_il(g, x, r, p, d, rr_new, rr_new_n, pd, nbp, ps, rr_old, batch, st))) return rc;
+        // alpha = rr/pd;  x += alpha p;  r -= alpha d;  rr' = ||r||^2   (the first update reads the start iterate)
+        const float *xi = it == 0 ? x_in : x;
+        if (SB == 1)
+            rc = scd_launch_cg_update_xr(xi, x, r, p, d, rr_new, rr_new_n, pd, nbp, ps, rr_old, batch, (int64_t)L.img, st);
+        else
+            rc = scd_launch_cg_update_xr_il(g, xi, x, r, p, d, rr_new, rr_new_n, pd, nbp, ps, rr_old, batch, st);
+        if (rc) return rc;
         std::swap(rr_new, rr_old);                 // the kernel wrote the newest partials into the older array
         rr_old_n = rr_new_n;
         rr_new_n = nvec;
@@ -212,9 +220,12 @@ extern "C" int scd_cg(const scd_geom_t *g, float *x, const float *rhs, double ga
         if (n_iter == 0) return 0;                // the result is the start iterate (x is updated in place)
         char *w = (char *)work;
         cudaStream_t st = (cudaStream_t)stream;
-        if ((rc = scd_launch_il_pack(g, x, (float *)(w + L.il_x), rhs, (float *)(w + L.il_b), batch, st))) return rc;
-        if ((rc = cg_run_il(g, L, (float)gamma, n_iter, batch, w, st))) return rc;
-        return scd_launch_il_unpack(g, (const float *)(w + L.il_x), x, batch, st);
+        if (scd_group_samples(g, batch) == 1 && (((uintptr_t)x | (uintptr_t)rhs) & 15) == 0)
+            return cg_run_il(g, L, x, x, rhs, (float)gamma, n_iter, batch, w, st);      // the layouts coincide: in place
+        float *xi = (float *)(w + L.il_x), *bi = (float *)(w + L.il_b);
+        if ((rc = scd_launch_il_pack(g, x, xi, rhs, bi, batch, st))) return rc;
+        if ((rc = cg_run_il(g, L, xi, xi, bi, (float)gamma, n_iter, batch, w, st))) return rc;
+        return scd_launch_il_unpack(g, xi, x, batch, st);
     }
     return scd_cg_run(g, x, x, rhs, (float)gamma, n_iter, batch, work, work_bytes, (cudaStream_t)stream, nullptr);
 }
@@ -379,11 +390,18 @@ extern "C" int scd_dds_step(const scd_geom_t *g, const float *x, const float *s,
         // Tweedie writes xhat0 for the caller and the CG start iterate / right-hand side as il images; DDIM reads
         // the CG result in that layout: 1 + 2 + 3*n_iter + 1 launches
         if ((rc = cg_check(g, work, work_bytes, n_iter, L, "scd_dds_step"))) return rc;
-        if ((rc = scd_launch_tweedie_il(g, x, s, atb, t, abar, n_table, (float)gamma, xhat0, (float *)(w + L.il_x),
-                                        (float *)(w + L.il_b), batch, st))) return rc;
-        if (n_iter > 0 && (rc = cg_run_il(g, L, (float)gamma, n_iter, batch, w, st))) return rc;
-        return scd_launch_ddim_il(g, (const float *)(w + L.il_x), s, eps, t, t_prev, abar, n_table, (float)eta,
-                                  (float)(eta * eta), x_next, batch, st);
+        float *xi = (float *)(w + L.il_x), *bi = (float *)(w + L.il_b);
+        if (scd_group_samples(g, batch) == 1) {
+            // one sample per group: il image = reference layout.  xhat0 (returned to the caller) is the start iterate,
+            // read only; the first update writes the iterate into the workspace
+            if ((rc = scd_launch_tweedie_rhs(x, s, atb, t, abar, n_table, (float)gamma, xhat0, bi, batch, (int64_t)L.img, st))) return rc;
+            if (n_iter > 0 && (rc = cg_run_il(g, L, xhat0, xi, bi, (float)gamma, n_iter, batch, w, st))) return rc;
+            return scd_launch_ddim(n_iter > 0 ? xi : xhat0, s, eps, t, t_prev, abar, n_table, (float)eta, (float)(eta * eta),
+                                   x_next, batch, (int64_t)L.img, st);
+        }
+        if ((rc = scd_launch_tweedie_il(g, x, s, atb, t, abar, n_table, (float)gamma, xhat0, xi, bi, batch, st))) return rc;
+        if (n_iter > 0 && (rc = cg_run_il(g, L, xi, xi, bi, (float)gamma, n_iter, batch, w, st))) return rc;
+        return scd_launch_ddim_il(g, xi, s, eps, t, t_prev, abar, n_table, (float)eta, (float)(eta * eta), x_next, batch, st);
     }
     float *b = (float *)(w + L.off_b), *xh = (float *)(w + L.off_xh);
     const int64_t numel = (int64_t)L.img;

@@ -91,6 +91,7 @@ struct MqParams {
     int tma;
     int spitch[2], nbox[2], bw[2];
     const float *zero_row;   // >= max(n0, n1) * 16 zero floats (source of the strip rows beyond the image)
+    int lead;                // pixels before pixel 0 in a row-major class-0 strip row (bulk rows need a 16-byte aligned start)
     int cls0_pm;             // class 0 fetched pixel-major by tensor copies too (4-D map tm0) instead of row-major bulk rows
     // output recurrence of the CG solve (acc_mode != 0): q = A r + beta q_old with
     // beta = sum(rr_new_part) / sum(rr_old_part) per sample (q_{k} = A p_k, p_k = r_k + beta p_{k-1});
@@ -341,7 +342,7 @@ __device__ __forceinline__ void mq_march_rows(float (&acc)[NSLOT][V], const int 
                                               int warp, int lane, int nst, int NBUF, int r_begin, int ncols,
                                               unsigned row_bytes, unsigned strip_bytes, unsigned char *tile0,
                                               const float2 *rays, unsigned long long *full, unsigned long long *empty,
-                                              unsigned long long *dbg)
+                                              unsigned long long *dbg, unsigned lane_shift)
 {
     typedef MqVec<V> LD;
     typedef typename LD::T VT;
@@ -360,7 +361,7 @@ __device__ __forceinline__ void mq_march_rows(float (&acc)[NSLOT][V], const int 
     const float zmax = (float)(ncols + 1);    // u = ncols: both taps on the right pads
     // shared-window address of this lane's samples in pixel 0 of row 0 of buffer 0, with the
     // mantissa offset of the floor trick folded in
-    const unsigned lane_base = mq_smem_u32(tile0) + (unsigned)(lq * V * 4) - (unsigned)MQ_MAGIC_BITS * PS;
+    const unsigned lane_base = mq_smem_u32(tile0) + (unsigned)(lq * V * 4) - (unsigned)MQ_MAGIC_BITS * PS + lane_shift;
     const unsigned rays_base = mq_smem_u32(rays);
     int bi = 0; unsigned ph = 0;
     for (int st = 0; st < nst; ++st) {
@@ -488,13 +489,14 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const
         MqAng a; a.scale = t.x; a.id = __float_as_int(t.y); ang[tid] = a;
     }
     if (P.tma && cls == 0 && !P.cls0_pm) {
-        // pad pixels (1 left, >= 2 right) of every row of every ring buffer: zero once, the row copies never touch them
-        const int padr = pitch - 1 - ncols;
-        const int per_row = (1 + padr) * SB;
+        // pad pixels (`lead` left, >= 2 right) of every row of every ring buffer: zero once, the row copies never touch them
+        const int lead = P.lead;
+        const int padr = pitch - lead - ncols;
+        const int per_row = (lead + padr) * SB;
         for (int i = tid; i < NBUF * TR * per_row; i += NTHR) {
             const int row = i / per_row, k = i - row * per_row;
             float *rp = reinterpret_cast<float *>(tile0 + (size_t)row * row_bytes);
-            rp[k < SB ? k : (size_t)(ncols + 1) * SB + (k - SB)] = 0.f;
+            rp[k < lead * SB ? k : (size_t)(ncols + lead) * SB + (k - lead * SB)] = 0.f;
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic-proxy writes vs the async copies
     }
@@ -532,7 +534,7 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const
             // the pad pixels of every ring buffer were zeroed above and are never overwritten.  Rows beyond the image
             // (the row count is rounded up to x8) are copied from a zero row.
             const bool mine = lane < TR;
-            const unsigned dst0 = mq_smem_u32(tile0) + (unsigned)lane * row_bytes + (unsigned)(SB * 4);
+            const unsigned dst0 = mq_smem_u32(tile0) + (unsigned)lane * row_bytes + (unsigned)(P.lead * SB * 4);
             const unsigned nbytes = (unsigned)ncols * (unsigned)(SB * 4);
             const float *img0 = P.img + (size_t)grp * nrows * ncols * SB;
             int bi = 0; unsigned ph = 0;
@@ -616,10 +618,12 @@ fp_march_kernel(const MqParams P, const __grid_constant__ CUtensorMap tm0, const
         }
         if (P.tma && (cls == 1 || P.cls0_pm))
             mq_march_rows<V, LPR, NSLOT, TR, NW, true>(acc, eidx, livemask, NCH, warp, lane, nst, NBUF, r_begin, ncols,
-                                                       row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg);
+                                                       row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg, 0u);
         else
+            // row-major strips of the bulk-row source start `lead` pixels into the row (pixel p sits at index p + lead)
             mq_march_rows<V, LPR, NSLOT, TR, NW, false>(acc, eidx, livemask, NCH, warp, lane, nst, NBUF, r_begin, ncols,
-                                                        row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg);
+                                                        row_bytes, strip_bytes, tile0, rays, full, empty, P.dbg,
+                                                        (P.tma && cls == 0) ? (unsigned)((P.lead - 1) * SB * 4) : 0u);
     }
     __syncthreads();                              // all strips consumed: the ring can be reused
     scd_stamp(P.dbg, 4);                          // march done
@@ -722,12 +726,14 @@ struct MqConfig {
 // Strip-row geometry of the tensor-copy path: ncols + 3 pixels (1 zero pixel left, 2 right) split into boxes of at
 // most 256 pixels (the box limit of a tensor map) whose byte size is a multiple of 128 (alignment of the copy's
 // shared-memory destination)
+static int mq_lead(int SB) { return SB >= 4 ? 1 : 4 / SB; }      // bulk rows start 16-byte aligned behind the pad pixels
+
 static void mq_tma_rows(const scd_geom *g, int SB, int spitch[2], int nbox[2], int bw[2])
 {
     const int nc[2] = {g->n1, g->n0};
     const int gran = std::max(1, 32 / SB);
     for (int c = 0; c < 2; ++c) {
-        const int need = nc[c] + 3;
+        const int need = nc[c] + 2 + (c == 0 ? mq_lead(SB) : 1);
         nbox[c] = (need + 255) / 256;
         int w = (need + nbox[c] - 1) / nbox[c];
         w = ((w + gran - 1) / gran) * gran;
@@ -1156,14 +1162,14 @@ int scd_launch_fp_ilimg(const scd_geom *g, const float *img_il, float *sino, flo
     }
     if (angle_lo == angle_hi) return 0;
     if (!scd_il_image_ok(g, batch)) { scd_set_error("scd_fp: no tensor-copy path for this batch / image size"); return SCD_E_INVALID; }
-    if (((uintptr_t)img_il & 127) != 0) { scd_set_error("scd_fp: interleaved image must be 128-byte aligned"); return SCD_E_INVALID; }
+    if (((uintptr_t)img_il & 15) != 0) { scd_set_error("scd_fp: interleaved image must be 16-byte aligned"); return SCD_E_INVALID; }
     int ncls[2] = {0, 0};
     for (int a = angle_lo; a < angle_hi; ++a) ncls[g->h_fp[a].cls]++;
     MqConfig c = mq_choose(g, batch, std::max(ncls[0], ncls[1]), true);
     if (c.smem > (size_t)g->smem_optin || !c.NSLOT) { scd_set_error("scd_fp: image too large for the shared-memory strip"); return SCD_E_INVALID; }
     MqParams P;
     mq_fill_params(g, c, P, sino, sino_il, batch, ncls);
-    P.img = img_il; P.zero_row = g->d_zero_row;
+    P.img = img_il; P.zero_row = g->d_zero_row; P.lead = mq_lead(c.SB);
     if (acc) {
         P.acc_mode = 1;
         P.rr_new_part = acc->rr_new_part; P.rr_new_n = acc->rr_new_n;
@@ -1190,7 +1196,11 @@ bool scd_il_image_ok(const scd_geom *g, int batch)
     if (!g || batch <= 0) return false;
     if (g->tune_fp_source == 1) return false;          // tuning: force the packed-copy path
     const int SB = scd_group_samples(g, batch);
-    if (SB < 4 || !mq_encoder()) return false;
+    if (!mq_encoder()) return false;
+    // a single sample per group: the interleaved image IS the reference layout; rows and the TR-row pieces of the
+    // class-1 gather are multiples of 16 bytes when n1 is a multiple of 4.  Pairs (SB = 2) have no interleaving
+    // kernels: they keep the packed copy.
+    if (SB == 2 || (SB == 1 && ((g->n1 & 3) || g->tune_fp_source == 2))) return false;
     int sp[2], nb[2], bw[2];
     mq_tma_rows(g, SB, sp, nb, bw);
     return nb[1] <= 32;                                 // one lane of the producer warp per class-1 box
@@ -1226,6 +1236,8 @@ int scd_launch_fp(const scd_geom *g, const float *img, float *sino, float *sino_
             scd_set_error("scd_fp: scratch too small (%zu bytes given, %zu needed; see scd_fp_scratch_bytes)", scratch_bytes, need + 128);
             return SCD_E_WORKSPACE;
         }
+        if (SB == 1 && ((uintptr_t)img & 15) == 0)      // one sample per group: the image already is its interleaved form
+            return scd_launch_fp_ilimg(g, img, sino, sino_il, batch, angle_lo, angle_hi, st, nullptr);
         int rc = scd_launch_il_pack(g, img, (float *)sp, nullptr, nullptr, batch, st);
         if (rc) return rc;
         return scd_launch_fp_ilimg(g, (const float *)sp, sino, sino_il, batch, angle_lo, angle_hi, st, nullptr);

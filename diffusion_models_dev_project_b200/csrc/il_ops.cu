@@ -236,7 +236,7 @@ ddim_il_kernel(const float *__restrict__ xh_il, const float *__restrict__ sc, co
 #define ILV_U 4
 template <int SB>
 __global__ void __launch_bounds__(IL_THREADS)
-cg_update_xr_il_kernel(float *__restrict__ x, float *__restrict__ r, const float *__restrict__ p, const float *__restrict__ d,
+cg_update_xr_il_kernel(const float *x_in, float *x, float *__restrict__ r, const float *__restrict__ p, const float *__restrict__ d,
                        const float *__restrict__ rr_part, int rr_n, const float *__restrict__ pd_part, int pd_n,
                        int part_stride, float *__restrict__ rr_new_part, size_t group_f4, int batch)
 {
@@ -247,6 +247,7 @@ cg_update_xr_il_kernel(float *__restrict__ x, float *__restrict__ r, const float
     scd_pdl_trigger();
     const int grp = blockIdx.y;
     const size_t base = (size_t)grp * group_f4;
+    const float4 *xi4 = reinterpret_cast<const float4 *>(x_in) + base;
     float4 *x4 = reinterpret_cast<float4 *>(x) + base;
     float4 *r4 = reinterpret_cast<float4 *>(r) + base;
     const float4 *p4 = reinterpret_cast<const float4 *>(p) + base;
@@ -258,7 +259,7 @@ cg_update_xr_il_kernel(float *__restrict__ x, float *__restrict__ r, const float
 #pragma unroll
         for (int u = 0; u < ILV_U; ++u) {
             const size_t k = i + (size_t)u * step;
-            if (k < group_f4) { xv[u] = x4[k]; rv[u] = r4[k]; pv[u] = p4[k]; dv[u] = d4[k]; }
+            if (k < group_f4) { xv[u] = xi4[k]; rv[u] = r4[k]; pv[u] = p4[k]; dv[u] = d4[k]; }
         }
     };
     load_batch(i0);                                // in flight while the per-sample scalars are formed
@@ -359,6 +360,12 @@ int scd_launch_il_pack(const scd_geom *g, const float *a_user, float *a_il, cons
     if (batch <= 0) return 0;
     dim3 grid; int SB, rc;
     if ((rc = il_grid(g, batch, grid, SB))) return rc;
+    if (SB == 1) {                                  // one sample per group: the two layouts coincide
+        const size_t bytes = (size_t)batch * g->n0 * g->n1 * 4;
+        if (a_il != a_user) SCD_CUDA(cudaMemcpyAsync(a_il, a_user, bytes, cudaMemcpyDeviceToDevice, st));
+        if (b_user && b_il != b_user) SCD_CUDA(cudaMemcpyAsync(b_il, b_user, bytes, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     IL_DISPATCH(SB, SCD_CUDA(scd_launch_kernel(il_pack_kernel<SB_>, grid, dim3(IL_THREADS), 0, st, 0, a_user, a_il, b_user, b_il,
                                                g->n0, g->n1, batch)))
     SCD_LAUNCH_CHECK("il_pack_kernel");
@@ -370,6 +377,10 @@ int scd_launch_il_unpack(const scd_geom *g, const float *a_il, float *a_user, in
     if (batch <= 0) return 0;
     dim3 grid; int SB, rc;
     if ((rc = il_grid(g, batch, grid, SB))) return rc;
+    if (SB == 1) {
+        if (a_il != a_user) SCD_CUDA(cudaMemcpyAsync(a_user, a_il, (size_t)batch * g->n0 * g->n1 * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     IL_DISPATCH(SB, SCD_CUDA(scd_launch_kernel(il_unpack_kernel<SB_>, grid, dim3(IL_THREADS), 0, st, 0, a_il, a_user, g->n0, g->n1, batch)))
     SCD_LAUNCH_CHECK("il_unpack_kernel");
     return 0;
@@ -401,7 +412,7 @@ int scd_launch_ddim_il(const scd_geom *g, const float *xh_il, const float *s, co
     return 0;
 }
 
-int scd_launch_cg_update_xr_il(const scd_geom *g, float *x, float *r, const float *p, const float *d,
+int scd_launch_cg_update_xr_il(const scd_geom *g, const float *x_in, float *x, float *r, const float *p, const float *d,
                                const float *rr_part, int rr_n, const float *pd_part, int pd_n, int part_stride,
                                float *rr_new_part, int batch, cudaStream_t st)
 {
@@ -410,7 +421,7 @@ int scd_launch_cg_update_xr_il(const scd_geom *g, float *x, float *r, const floa
     const int groups = (batch + SB - 1) / SB;
     const size_t f4 = (size_t)g->n0 * g->n1 * SB / 4;
     dim3 grid(scd_il_vec_blocks(g, batch), groups);
-    IL_DISPATCH(SB, SCD_CUDA(scd_launch_kernel(cg_update_xr_il_kernel<SB_>, grid, dim3(IL_THREADS), 0, st, 0, x, r, p, d, rr_part, rr_n,
+    IL_DISPATCH(SB, SCD_CUDA(scd_launch_kernel(cg_update_xr_il_kernel<SB_>, grid, dim3(IL_THREADS), 0, st, 0, x_in, x, r, p, d, rr_part, rr_n,
                                                pd_part, pd_n, part_stride, rr_new_part, f4, batch)))
     SCD_LAUNCH_CHECK("cg_update_xr_il_kernel");
     return 0;

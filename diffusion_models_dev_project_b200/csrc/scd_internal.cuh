@@ -188,9 +188,9 @@ int scd_launch_tweedie_il(const scd_geom *g, const float *x, const float *s, con
 int scd_launch_ddim_il(const scd_geom *g, const float *xh_il, const float *s, const float *eps, const float *t,
                        const float *t_prev, const float *abar, int n_table, float eta, float eta2, float *out,
                        int batch, cudaStream_t st);
-// alpha = rr/pd;  x += alpha p;  r -= alpha d;  per-block partials of ||r||^2 -- all vectors il images
+// alpha = rr/pd;  x = x_in + alpha p;  r -= alpha d;  per-block partials of ||r||^2 -- all vectors il images
 int scd_il_vec_blocks(const scd_geom *g, int batch);           // partials per sample written by the kernel below
-int scd_launch_cg_update_xr_il(const scd_geom *g, float *x, float *r, const float *p, const float *d,
+int scd_launch_cg_update_xr_il(const scd_geom *g, const float *x_in, float *x, float *r, const float *p, const float *d,
                                const float *rr_part, int rr_n, const float *pd_part, int pd_n, int part_stride,
                                float *rr_new_part, int batch, cudaStream_t st);
 size_t scd_fp_scratch_need(const scd_geom *g, int batch);

@@ -305,7 +305,8 @@ class B200RayTrafo(BaseRayTrafo):
 
     # ------------------------------------------- sample-interleaved images ---
     def il_supported(self, batch: int, device) -> bool:
-        """Whether batches of this size have an interleaved-image form (>= 3 samples: groups of >= 4)."""
+        """Whether batches of this size have an interleaved-image form: >= 3 samples (groups of >= 4), or a single
+        sample when the image width is a multiple of 4 (its interleaved image is the reference layout itself)."""
         h = self._handle(torch.device(device))
         return int(h._lib.scd_img_il_bytes(h.ptr, int(batch))) > 0
 

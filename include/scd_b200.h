@@ -110,7 +110,8 @@ int scd_bp_il(const scd_geom_t *g, const float *sino_il, float *out, int batch,
  * store per lane; scd_cg / scd_dds_step keep x, r, p, d in it for the whole solve.  A caller that iterates
  * with A / A* itself can do the same:
  *   scd_img_il_bytes   bytes of one il image for `batch` samples; 0 if this batch size has no il form
- *                      (1 or 2 samples: pixels below the 16-byte granule of a tensor copy)
+ *                      (2 samples; 1 sample when n1 is not a multiple of 4).  For ONE sample the il image is the
+ *                      [n0][n1] image itself: scd_fp / scd_cg / scd_dds_step then read the caller's tensors directly
  *   scd_img_il_pack / scd_img_il_unpack   [batch][n0][n1] <-> il image
  *   scd_fp_ilimg       sino_il = A(img_il)                                   -- ONE launch (fp_march)
  *   scd_bp_ilimg       out_il = c_acc * BP(sino_il) + c_add * addend_il      -- ONE launch (bp_tile)
@@ -257,7 +258,7 @@ void    scd_launch_count_reset(void);
 /* Override launch heuristics (tuning / tests).  key is one of
  * "fp_samples" (samples interleaved per pixel/bin: 1,2,4,8,16), "fp_angles", "fp_rows",
  * "fp_threads", "fp_nbuf", "fp_cluster", "fp_plan", "fp_source" (1 = packed copy + 1-D bulk copies for every
- * batch size instead of tensor copies from the interleaved image), "fp_cls0" (class-0 strips pixel-major through
+ * batch size instead of tensor copies from the interleaved image, 2 = only for single-sample groups), "fp_cls0" (class-0 strips pixel-major through
  * tensor copies: 1 = always, 2 = never), "fp_plan_cost" (fixed cost of a unit in the unit plan, percent of one angle), "bp_tile", "bp_share" (1 = plain
  * march, no tap sharing between the pixels of a column pair), "bp_rows" (rows in use per tile; 1 = always the
  * full tile); value 0

@@ -82,7 +82,7 @@ def test_fp_bp_other_shapes(im_shape, num_angles):
                                   dict(fp_samples=16, fp_angles=4, fp_rows=4, fp_threads=768), dict(fp_samples=8, fp_angles=3, fp_rows=8, fp_threads=768, fp_cluster=2), dict(fp_samples=4, fp_threads=768),
                                   dict(fp_samples=4, bp_tile=16), dict(fp_samples=2, bp_tile=32),
                                   dict(fp_samples=4, fp_source=1), dict(fp_samples=8, fp_source=1, fp_cluster=2), dict(fp_samples=16, fp_source=1, fp_rows=2),
-                                  dict(fp_samples=4, fp_cls0=1), dict(fp_samples=8, fp_cls0=2), dict(fp_samples=16, fp_cls0=1, fp_rows=2), dict(fp_samples=16, fp_cls0=1, fp_cluster=2)])
+                                  dict(fp_samples=1, fp_source=2), dict(fp_samples=1, fp_source=1, fp_angles=2), dict(fp_samples=4, fp_cls0=1), dict(fp_samples=8, fp_cls0=2), dict(fp_samples=16, fp_cls0=1, fp_rows=2), dict(fp_samples=16, fp_cls0=1, fp_cluster=2)])
 def test_tuning_variants_agree(tune):
     """Every template instantiation (samples per thread, rays per thread, tile shape) computes the same thing."""
     geom = O.OracleGeometry((96, 96), 20)
@@ -329,7 +329,8 @@ def test_interleaved_image_path(im_shape, num_angles, batch):
     (no packed copy), A* writing the interleaved layout -- against the oracle and against the packed-copy path."""
     geom = O.OracleGeometry(im_shape, num_angles)
     rt = _rt(im_shape, num_angles)
-    assert rt.il_supported(batch, 'cuda') and not rt.il_supported(2, 'cuda') and not rt.il_supported(1, 'cuda')
+    assert rt.il_supported(batch, 'cuda') and not rt.il_supported(2, 'cuda')
+    assert rt.il_supported(1, 'cuda') == (im_shape[1] % 4 == 0)        # one sample per group: il image = reference layout
     rng = np.random.default_rng(11)
     x = torch.from_numpy(rng.random((batch, 1, *im_shape), dtype=np.float32)).cuda()
     x_il = rt._img_il(x)
@@ -366,3 +367,33 @@ def test_pair_march_is_bit_identical_to_the_plain_march(im_shape, num_angles, ba
     z_plain = rt.trafo_adjoint(y)
     rt.set_tuning('cuda', bp_share=0)
     assert torch.equal(z, z_plain)
+
+
+@pytest.mark.parametrize('im_shape,num_angles', [((256, 256), 60), ((96, 72), 13), ((64, 200), 7), ((501, 500), 24)])
+def test_single_sample_on_the_tensor_copy_path(im_shape, num_angles):
+    """Batch 1 (BASELINE configs 1 and 5): with one sample per group the interleaved image is the reference layout,
+    so A reads the caller's tensor directly (bulk rows behind 4 lead pixels, class 1 gathered in 32-byte pieces) --
+    no packed copy, and CG runs 3 launches per iteration.  Against the oracle, the packed-copy path and the reference
+    cg recurrences."""
+    import diffusion_models_dev_project_b200 as pkg
+    geom = O.OracleGeometry(im_shape, num_angles)
+    rt = _rt(im_shape, num_angles)
+    assert rt.il_supported(1, 'cuda')
+    rng = np.random.default_rng(4)
+    x = torch.from_numpy(rng.random((1, 1, *im_shape), dtype=np.float32)).cuda()
+    y = rt(x)
+    assert rel_l2(y.cpu().numpy(), O.fp(geom, x.cpu().numpy())) < TOL
+    rt.set_tuning('cuda', fp_source=2)                    # packed copy for single-sample groups
+    y_packed = rt(x)
+    rhs = x + 0.5
+    sol_packed = pkg.cg(op=rt.normal_op(0.05), x=x, rhs=rhs, n_iter=3)
+    rt.set_tuning('cuda', fp_source=0)
+    assert rel_l2(y.cpu().numpy(), y_packed.cpu().numpy()) < 1e-6
+    from diffusion_models_dev_project_b200 import fused
+    fused.launch_count(reset=True)
+    sol = pkg.cg(op=rt.normal_op(0.05), x=x, rhs=rhs, n_iter=3)
+    assert fused.launch_count() == 2 + 3 * 3              # init (A, A*) + 3 x (A, A*, update): no pack, no copies
+    assert rel_l2(sol.cpu().numpy(), sol_packed.cpu().numpy()) < 1e-5
+    # unaligned view of the caller: falls back to a copy, same result
+    xx = torch.zeros(im_shape[0] * im_shape[1] + 1, device='cuda')[1:].view(1, 1, *im_shape).copy_(x[0, 0])
+    assert rel_l2(rt(xx).cpu().numpy(), y.cpu().numpy()) < 1e-6
