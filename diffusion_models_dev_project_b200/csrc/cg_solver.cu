@@ -7,13 +7,14 @@
 //   repeat n_iter: d = op(p); alpha = rr/<p,d>; x += alpha p; r -= alpha d;
 //                  rr' = ||r||^2; beta = rr'/rr; p = r + beta p
 // with op(v) = v + gamma*A*(A v) (src/samplers/utils.py:188-189).
-// Groups of >= 4 samples (batch >= 3): the vectors x, r, p, d, b are sample-interleaved images for the whole
+// Groups of >= 4 samples (batch >= 3) and batch 1 (whose interleaved image is the reference layout): the vectors
+// x, r, p, d, b are sample-interleaved images for the whole
 // solve (il_ops.cu) and an iteration is THREE launches with no packed copy of anything:
 //   fp_march   q = A r + beta q          (q_k = A p_k with p_k = r_k + beta p_{k-1}: the projector reads r through
 //                                         tensor copies, its output phase carries the recurrence and forms beta)
 //   bp_tile    p = r + beta p;  d = p + gamma A*(q);  partial <p,d>      (all in the backprojector's epilogue)
 //   cg_update_xr_il   alpha = rr/<p,d>;  x += alpha p;  r -= alpha d;  partial ||r||^2
-// Batches of 1 or 2 samples (pixels below the 16-byte granule of a tensor copy) keep the packed-copy sequence:
+// Batches of 2 samples (and batch 1 when n1 is not a multiple of 4) keep the packed-copy sequence:
 // fp_packq (p-update fused), fp_march, bp_tile(+axpy,+<p,d>), cg_update_xr (the last p-update is skipped).
 #include "scd_internal.cuh"
 #include <algorithm>

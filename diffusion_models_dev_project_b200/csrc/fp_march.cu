@@ -21,7 +21,7 @@
 //   strips        TR rows of the packed image = one contiguous byte range, fetched by a
 //                 producer warp with cp.async.bulk (TMA unit) into an mbarrier ring
 //                 (full/empty barriers; no CTA-wide barrier inside the march).
-//   il image      groups of >= 4 samples need no packed copy at all: the image is kept
+//   il image      groups of >= 4 samples (and a single sample) need no packed copy at all: the image is kept
 //                 sample-interleaved, img_il[group][k0][k1][SB] (no pads).  Class 0 (strip rows = image
 //                 rows): a row is one contiguous byte range -> one 1-D bulk copy per strip row into the
 //                 row-major strip [row][pixel][SB] of the packed path (pad pixels zeroed once in shared
