@@ -27,39 +27,41 @@ def simulate(x: Tensor, ray_trafo, white_noise_rel_stddev: float, rng=None,
 
 
 class SimulatedDataset(torch.utils.data.Dataset):
-    """``(noisy_observation, x, filtbackproj)`` triples of an image dataset (reference :25-74):
-    per-item seeds ``use_fixed_seeds_starting_from + idx`` unless a generator is passed."""
+    """Lazily simulated measurements of an image dataset: item ``k`` is the triple
+    ``(y_k, x_k, fbp(y_k))`` with ``y_k = simulate(x_k)`` (contract of the reference class,
+    src/physics/simulation.py:25-74, which the drivers iterate and index).
+
+    Noise is reproducible per item: unless a generator is shared across items (``rng``), item ``k`` draws from
+    ``numpy.random.default_rng(use_fixed_seeds_starting_from + k)`` (``None`` = fresh entropy); passing both a
+    generator and a seed base is refused like in the reference."""
 
     def __init__(self, image_dataset, ray_trafo, white_noise_rel_stddev: float,
                  use_fixed_seeds_starting_from: Optional[int] = 1,
                  rng: Optional[np.random.Generator] = None, device: Optional[Any] = None):
         super().__init__()
-        if rng is not None and use_fixed_seeds_starting_from is not None:
-            raise AssertionError('must not use fixed seeds when passing a custom rng')
-        self.image_dataset = image_dataset
-        self.ray_trafo = ray_trafo
+        assert rng is None or use_fixed_seeds_starting_from is None, \
+            'must not use fixed seeds when passing a custom rng'
+        self.image_dataset, self.ray_trafo, self.device = image_dataset, ray_trafo, device
         self.white_noise_rel_stddev = white_noise_rel_stddev
-        self.rng = rng
-        self.use_fixed_seeds_starting_from = use_fixed_seeds_starting_from
-        self.device = device
+        self.use_fixed_seeds_starting_from, self.rng = use_fixed_seeds_starting_from, rng
+
+    def _rng_for(self, k: int) -> np.random.Generator:
+        if self.rng is not None:
+            return self.rng
+        base = self.use_fixed_seeds_starting_from
+        return np.random.default_rng(base + k if base is not None else None)
+
+    def _triple(self, k: int, image: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        image = image.to(device=self.device)
+        y = simulate(image.unsqueeze(0), self.ray_trafo, self.white_noise_rel_stddev, rng=self._rng_for(k))
+        y = y.to(device=self.device)
+        return y[0], image, self.ray_trafo.fbp(y)[0].to(device=self.device)
 
     def __len__(self):
         return len(self.image_dataset)
 
-    def _generate_item(self, idx: int, x: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        rng = self.rng
-        if rng is None:
-            start = self.use_fixed_seeds_starting_from
-            rng = np.random.default_rng(None if start is None else start + idx)
-        x = x.to(device=self.device)
-        noisy = simulate(x[None], ray_trafo=self.ray_trafo, white_noise_rel_stddev=self.white_noise_rel_stddev,
-                         rng=rng)[0].to(device=self.device)
-        filtbackproj = self.ray_trafo.fbp(noisy[None])[0].to(device=self.device)
-        return noisy, x, filtbackproj
+    def __getitem__(self, k: int) -> Tuple[Tensor, Tensor, Tensor]:
+        return self._triple(k, self.image_dataset[k])
 
     def __iter__(self) -> Iterator[Tuple[Tensor, Tensor, Tensor]]:
-        for idx, x in enumerate(self.image_dataset):
-            yield self._generate_item(idx, x)
-
-    def __getitem__(self, idx: int) -> Tuple[Tensor, Tensor, Tensor]:
-        return self._generate_item(idx, self.image_dataset[idx])
+        return (self._triple(k, image) for k, image in enumerate(self.image_dataset))
